@@ -1,0 +1,51 @@
+"""pytest configuration: registers the `gpu` marker and seeds every test (the reference's
+tests/conftest.py:8-48 does the same with SEED = 42)."""
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 42
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _seed_everything():
+    random.seed(SEED)
+    np.random.seed(SEED)
+    torch.manual_seed(SEED)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(SEED)
+    yield
+
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="session")
+def golden_mm():
+    return np.load(os.path.join(GOLDEN_DIR, "sparse_mm_cases.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_idx():
+    return np.load(os.path.join(GOLDEN_DIR, "index_cases.npz"))
