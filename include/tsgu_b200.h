@@ -1,0 +1,177 @@
+/*
+ * tsgu_b200.h -- C ABI of the B200-native sparse_mm hot path.
+ *
+ * Drop-in boundary for cai4cai/torchsparsegradutils' `sparse_mm` (reference
+ * torchsparsegradutils/sparse_matmul.py:8-234).  The reference has no FFI of its
+ * own: its boundary is the Python function `sparse_mm` + `SparseMatMul.apply`
+ * (sparse_matmul.py:129,132) whose arithmetic is delegated to torch ATen.  Each
+ * entry point below replaces one of those ATen call sites; the citation on each
+ * declaration names it.  INTEGRATION.md shows the ctypes binding a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; no torch types.  All pointers are DEVICE
+ *     pointers on the current CUDA device; `stream` is a cudaStream_t passed as
+ *     void*.  Every call is asynchronous on `stream`; nothing synchronises.
+ *   - The caller owns every buffer (inputs, outputs, workspace).  The library
+ *     never allocates, frees or retains pointers past return.
+ *   - Return value: 0 = OK; > 0 = a cudaError_t from launch; < 0 = argument
+ *     error (TSGU_ERR_*).  tsgu_error_string() decodes both ranges.
+ *   - Strides are in ELEMENTS.  Dense operands are addressed as
+ *       X[item, r, k] = X + item*bs + r*rs + k*cs.
+ *   - Sparse operands are "CSR batches":
+ *       row r of item t spans entries [ rowptr[t*rowptr_bstride + r]     + t*nnz_bstride,
+ *                                       rowptr[t*rowptr_bstride + r + 1] + t*nnz_bstride )
+ *     of colind / vals.  torch batched CSR (crow (b,n+1), col (b,nnz)) is
+ *     rowptr_bstride = n+1, nnz_bstride = nnz; one flat CSR over batch*n rows
+ *     (what the COO->CSR and transpose builders emit) is rowptr_bstride = n,
+ *     nnz_bstride = 0.  Column indices are local to the item (0 <= col < m).
+ *   - Re-entrant and thread-safe; no static per-process device.
+ */
+#ifndef TSGU_B200_H
+#define TSGU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSGU_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define TSGU_API __attribute__((visibility("default")))
+#else
+#define TSGU_API
+#endif
+
+/* value dtypes */
+enum { TSGU_F32 = 0, TSGU_F64 = 1, TSGU_BF16 = 2 };
+/* index dtypes */
+enum { TSGU_I32 = 0, TSGU_I64 = 1 };
+/* kernel selection (AUTO: nnz-imbalance heuristic done by the caller) */
+enum { TSGU_ALGO_AUTO = 0, TSGU_ALGO_ROWSPLIT = 1, TSGU_ALGO_MERGE = 2 };
+/* argument errors */
+enum {
+  TSGU_ERR_DTYPE = -1,      /* unknown value / index dtype enum              */
+  TSGU_ERR_SHAPE = -2,      /* negative size, K <= 0 with rows > 0, ...      */
+  TSGU_ERR_WORKSPACE = -3,  /* workspace pointer null or too small           */
+  TSGU_ERR_ALGO = -4,       /* unknown algo enum                             */
+  TSGU_ERR_RANGE = -5       /* sizes do not fit the requested index dtype    */
+};
+
+TSGU_API int tsgu_version(void);
+TSGU_API const char* tsgu_error_string(int code);
+/* Number of kernels this library has launched in the calling process (monotonic;
+ * bench.py reports the delta over the timed region as `gpu_launches`). */
+TSGU_API int64_t tsgu_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * SpMM:  C[t] = A[t] * B[t]                 replaces torch.sparse.mm(A, B)
+ *   forward   sparse_matmul.py:155   (A in CSR, or COO via tsgu_coo_to_csr + perm)
+ *   grad_B    sparse_matmul.py:229   (A^T via tsgu_csr_transpose: rowptrT/colindT + perm)
+ * `perm` (nullable, idx_dtype): value of stored entry e is vals[perm[e]] instead of vals[e].
+ * C is written row-major: C[t, r, k] = C + t*c_bs + r*ldc + k; every row is written (empty
+ * rows get zeros), so C needs no initialisation.
+ * Workspace: tsgu_spmm_workspace_bytes() (0 for ROWSPLIT).
+ * ---------------------------------------------------------------------------------- */
+TSGU_API int tsgu_spmm_csr(const void* rowptr, const void* colind, const void* vals, const void* perm,
+                  const void* B, void* C,
+                  int64_t batch, int64_t n, int64_t m, int64_t K,
+                  int64_t rowptr_bstride, int64_t nnz_bstride, int64_t nnz_total,
+                  int64_t b_bs, int64_t b_rs, int64_t b_cs,
+                  int64_t c_bs, int64_t ldc,
+                  int val_dtype, int idx_dtype, int algo,
+                  void* workspace, size_t workspace_bytes, void* stream);
+TSGU_API size_t tsgu_spmm_workspace_bytes(int64_t batch, int64_t n, int64_t K, int64_t nnz_total,
+                                 int val_dtype, int algo);
+
+/* ------------------------------------------------------------------------------------
+ * SDDMM:  out[dst(e)] = < G[t, r_e, :], B[t, c_e, :] >     for every stored entry e
+ *   replaces index_select x2 + mul + sum, sparse_matmul.py:201-205, and the row expansion
+ *   repeat_interleave(arange(n), diff(crow)) of sparse_matmul.py:190-192 (never materialised).
+ * `out_index` (nullable, idx_dtype): dst(e) = out_index[e], entries with out_index[e] < 0 are
+ * skipped (used to write COO gradients back in A's storage order); null: dst(e) = e.
+ * ---------------------------------------------------------------------------------- */
+TSGU_API int tsgu_sddmm_csr(const void* rowptr, const void* colind, const void* out_index,
+                   const void* G, const void* B, void* out,
+                   int64_t batch, int64_t n, int64_t m, int64_t K,
+                   int64_t rowptr_bstride, int64_t nnz_bstride, int64_t nnz_total,
+                   int64_t g_bs, int64_t g_rs, int64_t g_cs,
+                   int64_t b_bs, int64_t b_rs, int64_t b_cs,
+                   int val_dtype, int idx_dtype, int algo, void* stream);
+
+/* Order-agnostic COO variant: row/col are int64 arrays of length nnz (torch COO indices,
+ * sparse_matmul.py:184-185); out[e] = <G[row[e],:], B[col[e],:]>.  Also the kernel the
+ * solve/lstsq backwards would reuse (sparse_solve.py:216-235, sparse_lstsq.py:239-256). */
+TSGU_API int tsgu_sddmm_coo(const int64_t* row, const int64_t* col, const void* G, const void* B, void* out,
+                   int64_t nnz, int64_t K,
+                   int64_t g_rs, int64_t g_cs, int64_t b_rs, int64_t b_cs,
+                   int val_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Index builders (bit-exact integer work).
+ * ---------------------------------------------------------------------------------- */
+
+/* Stable lexicographic sort of COO coordinates; replaces torch.unique(sorted)+argsort,
+ * utils/utils.py:148-149 (_sort_coo_indices).  idx is int64 (ndim, nnz) with row stride idx_ld;
+ * dims[d] is the extent of coordinate d (ndim = 2: row,col; 3: batch,row,col).
+ * key_dims <= ndim: only the leading key_dims coordinates form the key (ndim-1 = sort by
+ * (batch,)row only, keeping storage order inside a row).  Outputs: perm (perm_dtype; position in
+ * the input of the k-th sorted entry) and, if non-null, sorted_idx (int64, (ndim, nnz), ld nnz). */
+TSGU_API int tsgu_coo_sort(const int64_t* idx, int ndim, int64_t nnz, int64_t idx_ld, const int64_t* dims,
+                  int key_dims, int64_t* sorted_idx, void* perm, int perm_dtype,
+                  void* workspace, size_t workspace_bytes, void* stream);
+TSGU_API size_t tsgu_coo_sort_workspace_bytes(int ndim, int64_t nnz, int perm_dtype);
+
+/* COO (already sorted, or sorted through `perm`) -> flat CSR over batch*n rows; replaces
+ * bincount+cumsum (utils/utils.py:228-231) and the per-batch Python loop of
+ * convert_coo_to_csr_indices_values (utils/utils.py:327-344).  rowptr_out has batch*n+1 entries
+ * (absolute offsets), colind_out[k] is the item-local column of the k-th sorted entry. */
+TSGU_API int tsgu_coo_to_csr(const int64_t* idx, int ndim, int64_t nnz, int64_t idx_ld,
+                    int64_t batch, int64_t n, const void* perm,
+                    void* rowptr_out, void* colind_out, int out_idx_dtype, void* stream);
+
+/* Histogram + scan: row indices (any order) -> crow; replaces _compress_row_indices
+ * (utils/utils.py:152-233).  Output dtype = input dtype. */
+TSGU_API int tsgu_compress_rows(const void* rows, int64_t nnz, int64_t n, void* crow_out, int idx_dtype,
+                       void* workspace, size_t workspace_bytes, void* stream);
+TSGU_API size_t tsgu_compress_rows_workspace_bytes(int64_t n, int idx_dtype);
+
+/* crow -> per-entry row index; replaces _demcompress_crow_indices (utils/utils.py:413-470). */
+TSGU_API int tsgu_decompress_crow(const void* crow, int64_t n, int64_t nnz, void* rows_out, int idx_dtype,
+                         void* stream);
+
+/* CSR batch -> CSR of the transposes, as one flat CSR over batch*m rows: rowptrT (batch*m+1,
+ * absolute), colindT (item-local row of A), permT (absolute position of the entry in A's
+ * colind/vals storage).  Stable (ties keep A's storage order), so for duplicate-free input it is
+ * the unique answer A.t().to_sparse_csr() gives.  No reference function exists: the transpose is
+ * implicit in A.t() at sparse_matmul.py:229 and redone by ATen on every backward. */
+TSGU_API int tsgu_csr_transpose(const void* rowptr, const void* colind,
+                       int64_t batch, int64_t n, int64_t m,
+                       int64_t rowptr_bstride, int64_t nnz_bstride, int64_t nnz_total, int idx_dtype,
+                       void* rowptrT, void* colindT, void* permT, int out_idx_dtype,
+                       void* workspace, size_t workspace_bytes, void* stream);
+TSGU_API size_t tsgu_csr_transpose_workspace_bytes(int64_t batch, int64_t m, int64_t nnz_total,
+                                          int out_idx_dtype);
+
+/* out[k] = in[perm[k]] for the value array (values[permutation], utils/utils.py:327,340). */
+TSGU_API int tsgu_gather_values(const void* in, const void* perm, void* out, int64_t count,
+                       int val_dtype, int idx_dtype, void* stream);
+
+/* Segmented sum of duplicate coordinates: out[u] = sum_{k in [seg[u], seg[u+1])} in[perm[k]]
+ * (what coalesce() does to values, utils/utils.py:580). */
+TSGU_API int tsgu_segment_sum_values(const void* in, const void* perm, const void* seg, void* out,
+                            int64_t nseg, int val_dtype, int idx_dtype, void* stream);
+
+/* Strided dense -> row-major contiguous (B.reshape(-1,K) copy of sparse_matmul.py:153 when B is a
+ * permuted view, e.g. from _batch_sparse_mv, distributions/sparse_multivariate_normal.py:96,100). */
+TSGU_API int tsgu_pack_dense(const void* src, void* dst, int64_t batch, int64_t rows, int64_t cols,
+                    int64_t s_bs, int64_t s_rs, int64_t s_cs, int64_t d_bs, int64_t d_ld,
+                    int val_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSGU_B200_H */

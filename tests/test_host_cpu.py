@@ -1,0 +1,141 @@
+"""CPU (`-m "not gpu"`): host logic, error contract and the C-ABI surface -- no compute calls."""
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+import torchsparsegradutils_b200 as tsgu
+from torchsparsegradutils_b200 import _native as nat
+from torchsparsegradutils_b200.utils import utils as U
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _coo(shape=(4, 6)):
+    return torch.eye(*shape).to_sparse_coo()
+
+
+# ---- exact validation messages, in the reference's order (tests/test_sparse_matmul.py:162-212) ----
+def test_error_not_tensors():
+    with pytest.raises(ValueError, match="Both A and B should be instances of torch.Tensor"):
+        tsgu.sparse_mm("not a tensor", torch.rand(6, 2))
+
+
+def test_error_dims():
+    with pytest.raises(ValueError, match="Both A and B should be at least 2-dimensional tensors"):
+        tsgu.sparse_mm(torch.rand(6).to_sparse(), torch.rand(6, 2))
+    with pytest.raises(ValueError, match="A and B must both be 2D or both be 3D tensors"):
+        tsgu.sparse_mm(_coo(), torch.rand(1, 6, 2))
+
+
+def test_error_layouts():
+    with pytest.raises(ValueError, match="A should be in either COO or CSR sparse format"):
+        tsgu.sparse_mm(_coo().to_sparse_csc(), torch.rand(6, 2))
+    with pytest.raises(ValueError, match="A should be in either COO or CSR sparse format"):
+        tsgu.sparse_mm(torch.rand(4, 6), torch.rand(6, 2))
+    with pytest.raises(ValueError, match=re.escape("B must be a dense (strided) tensor")):
+        tsgu.sparse_mm(_coo(), torch.rand(6, 2).to_sparse())
+
+
+def test_error_batch_and_inner():
+    A = torch.stack([_coo(), _coo()])
+    with pytest.raises(ValueError, match="If batched, A and B must have the same batch size"):
+        tsgu.sparse_mm(A, torch.rand(3, 6, 2))
+    with pytest.raises(ValueError, match=re.escape("Incompatible inner dimensions: A[..., 6] vs B[..., 5]")):
+        tsgu.sparse_mm(_coo(), torch.rand(5, 2))
+
+
+def test_cpu_tensors_fail_loudly():
+    # north_star: no CPU fallback -- valid CPU inputs are refused, not silently computed
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tsgu.sparse_mm(_coo(), torch.rand(6, 2))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        U._sort_coo_indices(torch.tensor([[1, 0], [0, 1]]))
+
+
+def test_utils_validation_messages():
+    with pytest.raises(TypeError, match="Expected a list of tensors"):
+        U.stack_csr(torch.eye(2).to_sparse_csr())
+    with pytest.raises(ValueError, match="Cannot stack empty list of tensors."):
+        U.stack_csr([])
+    with pytest.raises(ValueError, match="All tensors must have the same shape."):
+        U.stack_csr([torch.eye(2).to_sparse_csr(), torch.eye(3).to_sparse_csr()])
+    with pytest.raises(ValueError, match="All tensors must be in CSR layout."):
+        U.stack_csr([torch.eye(2).to_sparse_coo(), torch.eye(2).to_sparse_coo()])
+    with pytest.raises(TypeError, match="row_indices must be a torch.Tensor."):
+        U._compress_row_indices([0, 1], 3)
+    with pytest.raises(ValueError, match="row_indices must be 1D"):
+        U._compress_row_indices(torch.zeros(2, 2, dtype=torch.int64), 3)
+    with pytest.raises(TypeError, match="integer dtype"):
+        U._compress_row_indices(torch.zeros(2), 3)
+    with pytest.raises(ValueError, match="num_rows must be a positive integer."):
+        U._compress_row_indices(torch.zeros(2, dtype=torch.int64), 0)
+    with pytest.raises(ValueError, match="negative entries"):
+        U._compress_row_indices(torch.tensor([-1, 0]), 3)
+    with pytest.raises(ValueError, match="entries >= num_rows"):
+        U._compress_row_indices(torch.tensor([0, 3]), 3)
+    with pytest.raises(ValueError, match="at least 2 rows"):
+        U.convert_coo_to_csr_indices_values(torch.zeros(1, 4, dtype=torch.int64), 3)
+    with pytest.raises(ValueError, match="at most 3 rows"):
+        U.convert_coo_to_csr_indices_values(torch.zeros(4, 4, dtype=torch.int64), 3)
+    with pytest.raises(ValueError, match="Row indices must be less than num_rows"):
+        U.convert_coo_to_csr_indices_values(torch.tensor([[5, 0], [0, 1]]), 3)
+    with pytest.raises(ValueError, match="does not match number of indices"):
+        U.convert_coo_to_csr_indices_values(torch.tensor([[1, 0], [0, 1]]), 3, torch.rand(3))
+    with pytest.raises(ValueError, match="Unsupported layout"):
+        U.convert_coo_to_csr(torch.eye(2).to_sparse_csr())
+    with pytest.raises(ValueError, match="either be all sparse_coo or all sparse_csr"):
+        U.sparse_block_diag(torch.eye(2).to_sparse_coo(), torch.eye(2).to_sparse_csr())
+    with pytest.raises(TypeError, match="not as a list or tuple"):
+        U.sparse_block_diag([torch.eye(2).to_sparse_coo()])
+    with pytest.raises(ValueError, match="does not match"):
+        U.sparse_block_diag_split(torch.eye(4).to_sparse_coo(), (2, 2), (3, 3))
+
+
+def test_block_diag_roundtrip_host_logic():
+    # pure index arithmetic: runs on any device (tests/test_utils.py:137-156, :209-230 semantics)
+    for conv in (lambda t: t.to_sparse_coo(), lambda t: t.to_sparse_csr()):
+        mats = [torch.rand(4, 6).round(decimals=0) * torch.rand(4, 6), torch.rand(3, 2), torch.rand(5, 5)]
+        sp = [conv(m) for m in mats]
+        bd = U.sparse_block_diag(*sp)
+        assert torch.equal(bd.to_dense(), torch.block_diag(*mats))
+        parts = U.sparse_block_diag_split(bd, (4, 6), (3, 2), (5, 5))
+        for p, m in zip(parts, mats):
+            assert torch.equal(p.to_dense(), m)
+    st = U.stack_csr([torch.eye(3).to_sparse_csr(), (2 * torch.eye(3)).to_sparse_csr()])
+    assert st.shape == (2, 3, 3) and torch.equal(st.to_dense(), torch.stack([torch.eye(3), 2 * torch.eye(3)]))
+
+
+# ---- the C ABI: the library loads and exports exactly what include/tsgu_b200.h declares ----
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "tsgu_b200.h")).read()
+    return sorted(set(re.findall(r"TSGU_API[^;]*?\b(tsgu_\w+)\s*\(", text)))
+
+
+def test_header_binding_and_library_agree():
+    declared = _declared_symbols()
+    assert declared == sorted(nat.EXPORTED_SYMBOLS), "include/tsgu_b200.h and _native._SIGNATURES drifted apart"
+    L = nat.lib()  # sets argtypes for every symbol; AttributeError if one is missing
+    for name in declared:
+        assert hasattr(L, name)
+    assert L.tsgu_version() == 1
+    assert L.tsgu_error_string(-3).decode().startswith("tsgu: workspace")
+    assert nat.launch_count() >= 0
+    out = subprocess.run(["nm", "-D", "--defined-only", nat.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r" T (tsgu_\w+)", out)))
+    assert exported == declared, "only the declared C ABI may be exported"
+
+
+def test_library_is_sm100a_and_torch_free():
+    out = subprocess.run(["cuobjdump", "--list-elf", nat.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and not re.search(r"sm_(?!100a)\d+", out)
+    ldd = subprocess.run(["ldd", nat.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in ldd and "c10" not in ldd  # plain C ABI: no torch types or libraries behind it
+
+
+def test_pattern_cache_api():
+    tsgu.set_pattern_cache_capacity(4)
+    tsgu.clear_pattern_cache()
+    tsgu.set_pattern_cache_capacity(16)

@@ -1,0 +1,319 @@
+"""GPU parity proper: CUDA path vs the CPU oracle on seeded inputs, plus the reference's own test
+contract (tests/test_sparse_matmul.py) re-expressed against this implementation."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import TOL, rand_csr
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _np(t):
+    return t.detach().to(torch.float64 if t.dtype == torch.bfloat16 else t.dtype).cpu().numpy()
+
+
+def _oracle(A, B, G):
+    """fp64-accumulated oracle on the (upcast) inputs; bf16 is checked against the fp32-upcast oracle
+    as SURVEY 8(c) prescribes (the reference's CPU path cannot run bf16 CSR)."""
+    odt = np.float64 if A.dtype == torch.float64 else np.float32
+    Bn, Gn = _np(B).astype(odt), _np(G).astype(odt)
+    if A.layout == torch.sparse_csr:
+        return orc.sparse_mm_fwd_bwd("csr", tuple(A.shape), Bn, Gn, crow=_np(A.crow_indices()),
+                                     col=_np(A.col_indices()), values=_np(A.values()).astype(odt))
+    return orc.sparse_mm_fwd_bwd("coo", tuple(A.shape), Bn, Gn, indices=_np(A._indices()),
+                                 values=_np(A._values()).astype(odt))
+
+
+def _run(A, B, G):
+    from torchsparsegradutils_b200 import sparse_mm
+
+    A = A.detach().requires_grad_(True)
+    B = B.detach().requires_grad_(True)
+    C = sparse_mm(A, B)
+    C.backward(G)
+    return C.detach(), A.grad, B.grad
+
+
+def _check(A, B, G):
+    C, gA, gB = _run(A, B, G)
+    ref = _oracle(A, B, G)
+    tol = TOL[A.dtype]
+    f = lambda t: torch.from_numpy(_np(t).astype(np.float64))  # noqa: E731
+    torch.testing.assert_close(f(C), torch.from_numpy(ref["C"].astype(np.float64)), **tol)
+    torch.testing.assert_close(f(gB), torch.from_numpy(ref["gradB"].astype(np.float64)), **tol)
+    gv = gA.values() if A.layout == torch.sparse_csr else gA._values()
+    torch.testing.assert_close(f(gv), torch.from_numpy(ref["gradA_values"].astype(np.float64)), **tol)
+    if A.layout == torch.sparse_coo:
+        assert torch.equal(gA._indices().cpu(), torch.from_numpy(ref["gradA_indices"]))
+
+
+KS = [1, 2, 3, 4, 8, 10, 16, 32, 64, 96, 128, 256, 512, 640, 1024, 1100]
+
+
+@pytest.mark.parametrize("K", KS)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.bfloat16])
+def test_csr_vs_oracle_all_K(K, dtype):
+    """Every kernel variant (lanes-per-row x vectors-per-lane, scalar and 128-bit paths)."""
+    n, m = 193, 161
+    A = rand_csr(n, m, 9, dtype=dtype, index_dtype=torch.int32, seed=K, ragged=True)
+    B = torch.randn(m, K, device=DEV, dtype=dtype)
+    G = torch.randn(n, K, device=DEV, dtype=dtype)
+    _check(A, B, G)
+
+
+@pytest.mark.parametrize("index_dtype", [torch.int32, torch.int64])
+@pytest.mark.parametrize("K", [5, 128])
+def test_batched_csr_vs_oracle(index_dtype, K):
+    A = rand_csr(120, 77, 6, batch=5, index_dtype=index_dtype, seed=3)
+    B = torch.randn(5, 77, K, device=DEV)
+    G = torch.randn(5, 120, K, device=DEV)
+    _check(A, B, G)
+
+
+@pytest.mark.parametrize("K", [7, 64])
+@pytest.mark.parametrize("coalesced", [True, False])
+def test_coo_vs_oracle(K, coalesced):
+    n, m, nnz = 300, 211, 4000
+    g = torch.Generator().manual_seed(K)
+    flat = torch.randperm(n * m, generator=g)[:nnz]
+    idx = torch.stack([flat // m, flat % m])
+    if not coalesced:  # add duplicates and keep the shuffled storage order
+        idx = torch.cat([idx, idx[:, :500]], dim=1)
+    vals = torch.rand(idx.shape[1], generator=g)
+    A = torch.sparse_coo_tensor(idx.to(DEV), vals.to(DEV), (n, m))
+    if coalesced:
+        A = A.coalesce()
+    _check(A, torch.randn(m, K, device=DEV), torch.randn(n, K, device=DEV))
+
+
+@pytest.mark.parametrize("dups", [False, True])
+def test_ragged_batched_coo_vs_oracle(dups):
+    b, n, m, K = 4, 50, 40, 32
+    g = torch.Generator().manual_seed(11)
+    parts = []
+    for t, nnz in enumerate([300, 0, 17, 120]):
+        flat = torch.randperm(n * m, generator=g)[:nnz]
+        parts.append(torch.stack([torch.full((nnz,), t), flat // m, flat % m]))
+    idx = torch.cat(parts, dim=1)
+    if dups:
+        idx = torch.cat([idx, idx[:, 5:60]], dim=1)
+    idx = idx[:, torch.randperm(idx.shape[1], generator=g)]
+    A = torch.sparse_coo_tensor(idx.to(DEV), torch.rand(idx.shape[1], generator=g).to(DEV), (b, n, m))
+    _check(A, torch.randn(b, m, K, device=DEV), torch.randn(b, n, K, device=DEV))
+
+
+def test_long_rows_and_empty_rows():
+    """Rows far longer than a warp batch next to empty rows (row-split corner cases)."""
+    n, m, K = 64, 5000, 128
+    g = torch.Generator().manual_seed(5)
+    cnt = torch.zeros(n, dtype=torch.int64)
+    cnt[3], cnt[10], cnt[63] = 4097, 33, 1
+    crow = torch.zeros(n + 1, dtype=torch.int64)
+    crow[1:] = cnt.cumsum(0)
+    col = torch.cat([torch.randperm(m, generator=g)[:c].sort().values for c in cnt.tolist()])
+    A = torch.sparse_csr_tensor(crow.to(DEV), col.to(DEV), torch.rand(col.numel(), generator=g).to(DEV), (n, m))
+    _check(A, torch.randn(m, K, device=DEV), torch.randn(n, K, device=DEV))
+
+
+def test_strided_operands():
+    """B and the upstream gradient as transposed / permuted / expanded views
+    (distributions/sparse_multivariate_normal.py:93-100 hands sparse_mm exactly these)."""
+    from torchsparsegradutils_b200 import sparse_mm
+
+    n, S = 96, 32
+    A = rand_csr(n, n, 5, seed=9)
+    V = torch.randn(S, n, device=DEV, requires_grad=True)
+    out = sparse_mm(A, V.t()).t()  # (S, n): grad arrives transposed as well
+    ref = (A.to_dense().double() @ V.detach().double().t()).t()
+    torch.testing.assert_close(out.detach().double(), ref, rtol=1e-5, atol=1e-6)
+    out.sum().backward()  # expanded (stride-0) upstream gradient
+    gref = A.to_dense().double().t() @ torch.ones(n, S, device=DEV, dtype=torch.float64)
+    torch.testing.assert_close(V.grad.double(), gref.t(), rtol=1e-5, atol=1e-6)
+    Ab = rand_csr(n, n, 5, batch=3, seed=10)
+    Vb = torch.randn(S, 3, n, device=DEV)
+    outb = sparse_mm(Ab, Vb.permute(1, 2, 0)).permute(2, 0, 1)
+    refb = torch.einsum("bij,sbj->sbi", Ab.to_dense().double(), Vb.double())
+    torch.testing.assert_close(outb.double(), refb, rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------- the reference's own test contract, re-targeted
+TEST_DATA = [((4, 6), (6, 2), 8), ((8, 16), (16, 10), 32), ((7, 4), (4, 9), 14),
+             ((1, 4, 6), (1, 6, 2), 8), ((4, 8, 16), (4, 16, 10), 32), ((11, 7, 4), (11, 4, 9), 14)]
+
+
+def _rand_sparse(shape, nnz, layout, index_dtype, dtype, seed=0):
+    """Output contract of the reference's rand_sparse (unique coords, nnz per item, coalesced / sorted)."""
+    g = torch.Generator().manual_seed(seed)
+    b = shape[0] if len(shape) == 3 else 1
+    n, m = shape[-2:]
+    mats = []
+    for _ in range(b):
+        flat = torch.randperm(n * m, generator=g)[:nnz].sort().values
+        mats.append(torch.sparse_coo_tensor(torch.stack([flat // m, flat % m]), torch.rand(nnz, generator=g).to(dtype),
+                                            (n, m)).coalesce())
+    if layout == torch.sparse_coo:
+        A = torch.stack(mats).coalesce() if len(shape) == 3 else mats[0]
+        return A.to(DEV)
+    csrs = [t.to_sparse_csr() for t in mats]
+    crow = torch.stack([c.crow_indices() for c in csrs]) if len(shape) == 3 else csrs[0].crow_indices()
+    col = torch.stack([c.col_indices() for c in csrs]) if len(shape) == 3 else csrs[0].col_indices()
+    val = torch.stack([c.values() for c in csrs]) if len(shape) == 3 else csrs[0].values()
+    return torch.sparse_csr_tensor(crow.to(index_dtype).to(DEV), col.to(index_dtype).to(DEV), val.to(DEV), shape)
+
+
+@pytest.mark.parametrize("shapes", TEST_DATA, ids=lambda s: "x".join(map(str, s[0])))
+@pytest.mark.parametrize("layout", [torch.sparse_coo, torch.sparse_csr], ids=["coo", "csr"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("index_dtype", [torch.int32, torch.int64], ids=["i32", "i64"])
+def test_forward_backward_vs_dense(shapes, layout, dtype, index_dtype):
+    """tests/test_sparse_matmul.py:78-128 with the reference's tolerances tightened to north_star's."""
+    from torchsparsegradutils_b200 import sparse_mm
+
+    A_shape, B_shape, nnz = shapes
+    As = _rand_sparse(A_shape, nnz, layout, index_dtype, dtype, seed=nnz).requires_grad_()
+    Ad = As.detach().clone().to_dense().requires_grad_()
+    B1 = torch.rand(*B_shape, dtype=dtype, device=DEV).requires_grad_()
+    B2 = B1.detach().clone().requires_grad_()
+    r1, r2 = sparse_mm(As, B1), torch.matmul(Ad, B2)
+    tol = TOL[dtype]
+    torch.testing.assert_close(r1, r2, **tol)
+    go = torch.rand_like(r1)
+    r1.backward(go)
+    r2.backward(go)
+    assert As.grad.layout == layout
+    if layout is torch.sparse_csr or len(A_shape) == 2:
+        assert As.grad._nnz() == nnz
+    else:
+        assert As.grad._nnz() == nnz * A_shape[0]
+    if layout is torch.sparse_csr:
+        assert As.grad.crow_indices().dtype == index_dtype
+    mask = As.grad.to_dense() != 0.0
+    torch.testing.assert_close(As.grad.to_dense()[mask], Ad.grad[mask], **tol)
+    torch.testing.assert_close(B1.grad, B2.grad, **tol)
+
+
+@pytest.mark.parametrize("layout", [torch.sparse_coo, torch.sparse_csr], ids=["coo", "csr"])
+def test_conditional_gradients(layout):
+    """tests/test_sparse_matmul.py:134-157."""
+    from torchsparsegradutils_b200 import sparse_mm
+
+    A = _rand_sparse((5, 4), 6, layout, torch.int64, torch.float32)
+    B = torch.randn(4, 3, device=DEV)
+    A1, B1 = A.detach().clone(), B.detach().clone().requires_grad_()
+    sparse_mm(A1, B1).sum().backward()
+    assert A1.grad is None and B1.grad is not None
+    A2, B2 = A.detach().clone().requires_grad_(), B.detach().clone()
+    out = sparse_mm(A2, B2)
+    assert out.requires_grad
+    out.sum().backward()
+    assert A2.grad is not None and B2.grad is None
+    with torch.no_grad():
+        assert not sparse_mm(A2, B2).requires_grad
+    assert not sparse_mm(A.detach(), B.detach()).requires_grad
+
+
+def test_dtype_mismatch_is_runtime_error():
+    from torchsparsegradutils_b200 import sparse_mm
+
+    A = _rand_sparse((5, 4), 6, torch.sparse_csr, torch.int64, torch.float32)
+    with pytest.raises(RuntimeError, match="same dtype"):
+        sparse_mm(A, torch.randn(4, 3, device=DEV, dtype=torch.float64))
+
+
+@pytest.mark.parametrize("layout", [torch.sparse_coo, torch.sparse_csr], ids=["coo", "csr"])
+def test_multi_step_optimisation(layout):
+    """tests/test_sparse_matmul.py:295-338: A.grad values drive in-place SGD on A's values for 3 steps."""
+    from torchsparsegradutils_b200 import sparse_mm
+
+    A = _rand_sparse((12, 9), 30, layout, torch.int64, torch.float32).requires_grad_()
+    B = torch.randn(9, 4, device=DEV)
+    tgt = torch.randn(12, 4, device=DEV)
+    losses = []
+    for _ in range(3):
+        loss = ((sparse_mm(A, B) - tgt) ** 2).sum()
+        loss.backward()
+        losses.append(float(loss))
+        with torch.no_grad():
+            gv = A.grad._values() if layout == torch.sparse_coo else A.grad.values()
+            av = A._values() if layout == torch.sparse_coo else A.values()
+            av -= 1e-3 * gv
+        A.grad = None
+    assert B.grad is None and losses[2] < losses[0]
+
+
+def test_double_backward_raises():
+    """tests/test_sparse_matmul.py:363-376."""
+    from torchsparsegradutils_b200 import sparse_mm
+
+    A = _rand_sparse((6, 6), 10, torch.sparse_coo, torch.int64, torch.float32).requires_grad_()
+    B = torch.randn(6, 2, device=DEV, requires_grad=True)
+    loss = sparse_mm(A, B).sum()
+    loss.backward()
+    with pytest.raises(RuntimeError, match="second time"):
+        loss.backward()
+
+
+def test_non_leaf_sparse_input_routes_grad_to_values():
+    """README.md:145-156: A built from values that require grad."""
+    from torchsparsegradutils_b200 import sparse_mm
+
+    idx = torch.tensor([[0, 1, 1], [2, 0, 2]], device=DEV)
+    vals = torch.tensor([3.0, 4.0, 5.0], device=DEV, requires_grad=True)
+    B = torch.randn(3, 2, device=DEV)
+    sparse_mm(torch.sparse_coo_tensor(idx, vals, (2, 3)), B).sum().backward()
+    torch.testing.assert_close(vals.grad, B.sum(dim=1)[idx[1]])
+
+
+def test_quickstart_examples():
+    """tests/test_quickstart_guide.py:12-54 and the doctests at sparse_matmul.py:85-111."""
+    from torchsparsegradutils_b200 import sparse_mm
+
+    A = torch.tensor([[0, 1.0], [2.0, 0], [0, 3.0]], device=DEV).to_sparse().requires_grad_()
+    B = torch.randn(2, 2, device=DEV, requires_grad=True)
+    out = sparse_mm(A, B)
+    assert out.shape == (3, 2)
+    out.sum().backward()
+    assert A.grad.is_sparse and A.grad._nnz() == 3
+    Ab = torch.stack([A.detach(), A.detach()]).requires_grad_()
+    outb = sparse_mm(Ab, torch.randn(2, 2, 2, device=DEV))
+    assert outb.shape == (2, 3, 2)
+    outb.sum().backward()
+    assert Ab.grad.is_sparse and Ab.grad.sparse_dim() == 3
+    # known answer, Dockerfile.pip-install:47-52
+    K = torch.tensor([[2.0, 0.0], [3.0, 4.0]], device=DEV).to_sparse_coo()
+    assert torch.equal(sparse_mm(K, torch.tensor([[5.0], [7.0]], device=DEV)).cpu(), torch.tensor([[10.0], [43.0]]))
+
+
+def test_pattern_cache_sees_inplace_index_edits():
+    from torchsparsegradutils_b200 import sparse_mm
+
+    idx = torch.tensor([[0, 1], [0, 1]], device=DEV)
+    A = torch.sparse_coo_tensor(idx, torch.ones(2, device=DEV), (2, 2))
+    B = torch.tensor([[1.0, 2.0], [3.0, 4.0]], device=DEV)
+    assert torch.equal(sparse_mm(A, B), B)
+    idx[1] = torch.tensor([1, 0], device=DEV)  # same storage, new pattern: _version bumps
+    assert torch.equal(sparse_mm(A, B), B.flip(0))
+
+
+def test_memory_no_nnz_by_k_temporaries():
+    """tests/test_sparse_matmul.py:217-292 in spirit: fwd+bwd peak stays far below one nnz x K temporary
+    (the reference's backward materialises three of them)."""
+    from torchsparsegradutils_b200 import sparse_mm
+
+    n, K, per_row = 20000, 512, 16
+    A = rand_csr(n, n, per_row, seed=1).requires_grad_()
+    B = torch.randn(n, K, device=DEV, requires_grad=True)
+    G = torch.randn(n, K, device=DEV)
+    sparse_mm(A, B).backward(G)  # warm the pattern cache (transpose build)
+    A.grad = B.grad = None
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    sparse_mm(A, B).backward(G)
+    torch.cuda.synchronize()
+    extra = torch.cuda.max_memory_allocated() - base
+    one_temp = n * per_row * K * 4
+    assert extra < 0.25 * one_temp, (extra, one_temp)

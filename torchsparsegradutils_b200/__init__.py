@@ -1,0 +1,14 @@
+"""B200-native drop-in for the ``sparse_mm`` hot path of cai4cai/torchsparsegradutils.
+
+    from torchsparsegradutils_b200 import sparse_mm      # same signature as the reference's
+
+Only the path named by BASELINE.json's north_star lives here: ``sparse_mm`` / ``SparseMatMul`` and the
+index/layout helpers it depends on.  The arithmetic is hand-written sm_100a CUDA behind the C ABI in
+``include/tsgu_b200.h`` (``libtsgu_b200.so``); there is no CPU or PyTorch fallback.
+"""
+from . import utils
+from ._pattern import clear_pattern_cache, set_pattern_cache_capacity
+from .sparse_matmul import SparseMatMul, sparse_mm
+
+__all__ = ["sparse_mm", "SparseMatMul", "utils", "clear_pattern_cache", "set_pattern_cache_capacity"]
+__version__ = "0.1.0"

@@ -1,0 +1,135 @@
+"""Thin launchers: torch tensors in, C-ABI calls on the current stream, torch tensors out."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _native as nat
+from ._pattern import CsrPattern
+
+_VEC_ELEMS = {torch.float32: 4, torch.float64: 2, torch.bfloat16: 8}
+
+
+def _vector_ready(x: torch.Tensor) -> bool:
+    """Can the 128-bit kernels read this (batch, rows, K) operand in place?"""
+    epv = _VEC_ELEMS[x.dtype]
+    bs, rs, cs = x.stride()
+    K = x.shape[-1]
+    if K % epv:
+        return False
+    ok_rs = rs % epv == 0 or x.shape[1] <= 1
+    ok_bs = bs % epv == 0 or x.shape[0] <= 1
+    return (cs == 1 or K == 1) and ok_rs and ok_bs and x.data_ptr() % 16 == 0
+
+
+def pack_dense(x: torch.Tensor) -> torch.Tensor:
+    """Strided (batch, rows, K) -> contiguous, through tsgu_pack_dense (coalesced on both sides)."""
+    out = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+    b, r, k = x.shape
+    if out.numel() == 0:
+        return out
+    with torch.cuda.device(x.device):
+        nat.check(nat.lib().tsgu_pack_dense(x.data_ptr(), out.data_ptr(), b, r, k, x.stride(0), x.stride(1),
+                                            x.stride(2), r * k, k, nat.val_enum(x.dtype), nat.stream_ptr(x.device)),
+                  "tsgu_pack_dense")
+    return out
+
+
+def prepare_dense(x: torch.Tensor) -> torch.Tensor:
+    """Return a (batch, rows, K) operand the kernels can address.
+
+    Vectorisable K: make it 128-bit readable (pack once if it is a transposed / permuted / expanded
+    view, which is what ``_batch_sparse_mv`` hands us, distributions/sparse_multivariate_normal.py:96,100).
+    Other K: the scalar kernels take arbitrary element strides, no copy.
+    """
+    if x.shape[-1] % _VEC_ELEMS[x.dtype] == 0 and not _vector_ready(x):
+        return pack_dense(x)
+    return x
+
+
+def _as3d(x: torch.Tensor) -> torch.Tensor:
+    return x if x.dim() == 3 else x.unsqueeze(0)
+
+
+def _strides(x: torch.Tensor):
+    """Element strides with size-1 dims normalised, so they never disqualify the 128-bit path."""
+    bs, rs, cs = x.stride()
+    return (bs if x.shape[0] > 1 else 0, rs if x.shape[1] > 1 else 0, cs if x.shape[2] > 1 else 1)
+
+
+def spmm(pat: CsrPattern, vals: torch.Tensor, dense: torch.Tensor, algo: int = nat.ALGO_AUTO) -> torch.Tensor:
+    """out[t] = A[t] @ dense[t]; dense is (batch, m, K) (any strides); returns contiguous (batch, n, K)."""
+    dense = prepare_dense(_as3d(dense))
+    K = dense.shape[-1]
+    out = torch.empty((pat.batch, pat.n, K), dtype=dense.dtype, device=dense.device)
+    if out.numel() == 0:
+        return out
+    dev = dense.device
+    L = nat.lib()
+    vdt = nat.val_enum(dense.dtype)
+    with torch.cuda.device(dev):
+        ws_bytes = L.tsgu_spmm_workspace_bytes(pat.batch, pat.n, K, pat.nnz_total, vdt, algo)
+        ws = nat.workspace(ws_bytes, dev) if ws_bytes else None
+        nat.check(L.tsgu_spmm_csr(nat.ptr(pat.rowptr), nat.ptr(pat.colind), nat.ptr(vals), nat.ptr(pat.perm),
+                                  dense.data_ptr(), out.data_ptr(), pat.batch, pat.n, pat.m, K,
+                                  pat.rowptr_bstride, pat.nnz_bstride, pat.nnz_total,
+                                  *_strides(dense), pat.n * K, K,
+                                  vdt, pat.idx, algo, nat.ptr(ws), ws.numel() if ws is not None else 0,
+                                  nat.stream_ptr(dev)), "tsgu_spmm_csr")
+    return out
+
+
+def sddmm(pat: CsrPattern, G: torch.Tensor, B: torch.Tensor, out_index: Optional[torch.Tensor], nnz_out: int,
+          algo: int = nat.ALGO_AUTO) -> torch.Tensor:
+    """values[dst(e)] = <G[t, r_e], B[t, c_e]> for every stored entry of the pattern."""
+    G = prepare_dense(_as3d(G))
+    B = prepare_dense(_as3d(B))
+    out = torch.empty(nnz_out, dtype=B.dtype, device=B.device)
+    if nnz_out == 0:
+        return out
+    dev = B.device
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().tsgu_sddmm_csr(nat.ptr(pat.rowptr), nat.ptr(pat.colind), nat.ptr(out_index),
+                                           G.data_ptr(), B.data_ptr(), out.data_ptr(), pat.batch, pat.n, pat.m,
+                                           B.shape[-1], pat.rowptr_bstride, pat.nnz_bstride, pat.nnz_total,
+                                           *_strides(G), *_strides(B),
+                                           nat.val_enum(B.dtype), pat.idx, algo, nat.stream_ptr(dev)),
+                  "tsgu_sddmm_csr")
+    return out
+
+
+def sddmm_coo(row: torch.Tensor, col: torch.Tensor, G: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    """Order-agnostic SDDMM on raw int64 COO coordinates (2-D operands)."""
+    G = prepare_dense(_as3d(G))[0]
+    B = prepare_dense(_as3d(B))[0]
+    nnz = row.shape[0]
+    out = torch.empty(nnz, dtype=B.dtype, device=B.device)
+    if nnz == 0:
+        return out
+    row, col = row.contiguous(), col.contiguous()
+    with torch.cuda.device(B.device):
+        nat.check(nat.lib().tsgu_sddmm_coo(row.data_ptr(), col.data_ptr(), G.data_ptr(), B.data_ptr(), out.data_ptr(),
+                                           nnz, B.shape[-1], G.stride(0), G.stride(1), B.stride(0), B.stride(1),
+                                           nat.val_enum(B.dtype), nat.stream_ptr(B.device)), "tsgu_sddmm_coo")
+    return out
+
+
+def segment_sum_values(vals: torch.Tensor, perm: torch.Tensor, seg: torch.Tensor, nseg: int) -> torch.Tensor:
+    out = torch.empty(nseg, dtype=vals.dtype, device=vals.device)
+    if nseg:
+        with torch.cuda.device(vals.device):
+            nat.check(nat.lib().tsgu_segment_sum_values(vals.data_ptr(), nat.ptr(perm), seg.data_ptr(), out.data_ptr(),
+                                                        nseg, nat.val_enum(vals.dtype), nat.idx_enum(seg.dtype),
+                                                        nat.stream_ptr(vals.device)), "tsgu_segment_sum_values")
+    return out
+
+
+def gather_values(vals: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(perm.shape, dtype=vals.dtype, device=vals.device)
+    if out.numel():
+        with torch.cuda.device(vals.device):
+            nat.check(nat.lib().tsgu_gather_values(vals.data_ptr(), perm.data_ptr(), out.data_ptr(), perm.numel(),
+                                                   nat.val_enum(vals.dtype), nat.idx_enum(perm.dtype),
+                                                   nat.stream_ptr(vals.device)), "tsgu_gather_values")
+    return out

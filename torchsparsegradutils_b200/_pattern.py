@@ -1,0 +1,233 @@
+"""Sparsity-pattern descriptors and their cache.
+
+The reference rebuilds index structure on every call: a Python block-diagonal assembly for batched
+inputs (``utils/utils.py:474-645``), a ``repeat_interleave`` row expansion in every backward
+(``sparse_matmul.py:190-192``) and an implicit CSC->CSR re-sort inside ``torch.sparse.mm(A.t(), .)``
+(``sparse_matmul.py:229``).  Training loops keep the pattern fixed and only update the values
+(``tests/test_sparse_matmul.py:295-338``), so here every derived structure (COO->CSR order, the
+transpose) is built once per pattern by the index-builder kernels and cached.
+
+A cache entry keeps a reference to the index tensors it was built from, so their storage cannot be
+recycled for a different pattern while the entry lives, and it is invalidated by an in-place edit
+(``Tensor._version``).  Entries are evicted LRU; ``clear_pattern_cache()`` drops everything.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from collections import OrderedDict
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from . import _native as nat
+
+_CACHE_CAPACITY = 16
+_cache: "OrderedDict[tuple, object]" = OrderedDict()
+_cache_lock = threading.Lock()
+_I32_MAX = 2**31 - 1
+
+
+def clear_pattern_cache() -> None:
+    with _cache_lock:
+        _cache.clear()
+
+
+def set_pattern_cache_capacity(n: int) -> None:
+    global _CACHE_CAPACITY
+    _CACHE_CAPACITY = max(int(n), 0)
+    with _cache_lock:
+        while len(_cache) > _CACHE_CAPACITY:
+            _cache.popitem(last=False)
+
+
+@dataclass
+class CsrPattern:
+    """A batch of CSR matrices as the kernels consume it (see include/tsgu_b200.h conventions)."""
+
+    rowptr: torch.Tensor
+    colind: torch.Tensor
+    perm: Optional[torch.Tensor]  # value of entry e is vals.flatten()[perm[e]]
+    batch: int
+    n: int
+    m: int
+    rowptr_bstride: int
+    nnz_bstride: int
+    nnz_total: int
+    idx: int  # nat.I32 / nat.I64
+    keep: tuple = ()  # tensors whose storage must outlive this pattern (cache-key owners)
+    _transpose: Optional["CsrPattern"] = field(default=None, repr=False)
+    _lock: threading.Lock = field(default_factory=threading.Lock, repr=False)
+
+    @property
+    def device(self) -> torch.device:
+        return self.rowptr.device
+
+    def transpose(self) -> "CsrPattern":
+        """CSR of the transposes (flat over batch*m rows), built once by tsgu_csr_transpose."""
+        if self._transpose is None:
+            with self._lock:
+                if self._transpose is None:
+                    self._transpose = _build_transpose(self)
+        return self._transpose
+
+
+def _internal_idx(batch: int, rows: int, cols: int, nnz: int) -> int:
+    """Index width for structures we build ourselves: int32 whenever everything fits."""
+    return nat.I32 if max(batch * rows + 1, batch * cols + 1, nnz) < _I32_MAX else nat.I64
+
+
+def _build_transpose(p: CsrPattern) -> CsrPattern:
+    dev = p.device
+    out_idx = _internal_idx(p.batch, p.m, p.n, p.nnz_total)
+    odt = nat.IDX_TORCH[out_idx]
+    rowptrT = torch.empty(p.batch * p.m + 1, dtype=odt, device=dev)
+    colindT = torch.empty(p.nnz_total, dtype=odt, device=dev)
+    permT = torch.empty(p.nnz_total, dtype=odt, device=dev)
+    L = nat.lib()
+    with torch.cuda.device(dev):
+        ws_bytes = L.tsgu_csr_transpose_workspace_bytes(p.batch, p.m, p.nnz_total, out_idx)
+        ws = nat.workspace(ws_bytes, dev)
+        nat.check(L.tsgu_csr_transpose(nat.ptr(p.rowptr), nat.ptr(p.colind), p.batch, p.n, p.m, p.rowptr_bstride,
+                                       p.nnz_bstride, p.nnz_total, p.idx, nat.ptr(rowptrT), nat.ptr(colindT),
+                                       nat.ptr(permT), out_idx, nat.ptr(ws), ws.numel(), nat.stream_ptr(dev)),
+                  "tsgu_csr_transpose")
+    if p.perm is not None and p.nnz_total > 0:
+        # entries of p are themselves a permutation of the caller's value storage: compose once
+        permT = p.perm.to(odt).index_select(0, permT.long()) if p.perm.dtype != odt else p.perm.index_select(0, permT.long())
+    return CsrPattern(rowptrT, colindT, permT, p.batch, p.m, p.n, p.m, 0, p.nnz_total, out_idx, keep=(p,))
+
+
+def _cache_get(key):
+    with _cache_lock:
+        hit = _cache.get(key)
+        if hit is not None:
+            _cache.move_to_end(key)
+        return hit
+
+
+def _cache_put(key, value):
+    if _CACHE_CAPACITY == 0:
+        return
+    with _cache_lock:
+        _cache[key] = value
+        while len(_cache) > _CACHE_CAPACITY:
+            _cache.popitem(last=False)
+
+
+# ------------------------------------------------------------------------------------------ CSR
+def csr_pattern(A: torch.Tensor) -> CsrPattern:
+    """Pattern of a (batched) torch CSR tensor: a zero-copy view of its crow/col arrays."""
+    crow, col = A.crow_indices(), A.col_indices()
+    key = ("csr", crow.data_ptr(), col.data_ptr(), crow._version, col._version, tuple(A.shape), crow.dtype,
+           crow.device)
+    hit = _cache_get(key)
+    if hit is not None:
+        return hit
+    batched = A.dim() == 3
+    batch = A.shape[0] if batched else 1
+    n, m = A.shape[-2], A.shape[-1]
+    crow_c, col_c = crow.contiguous(), col.contiguous()
+    nnz_item = col_c.shape[-1]
+    pat = CsrPattern(crow_c, col_c, None, batch, n, m, n + 1, nnz_item, batch * nnz_item,
+                     nat.idx_enum(crow.dtype), keep=(crow, col))
+    _cache_put(key, pat)
+    return pat
+
+
+# ------------------------------------------------------------------------------------------ COO
+@dataclass
+class CooPattern:
+    """Derived structure of a COO tensor: a flat CSR over batch*n rows plus how to map values/grads."""
+
+    csr: CsrPattern
+    # unbatched: gradient values go back to storage order through out_index (= csr.perm) or identity
+    out_index: Optional[torch.Tensor]
+    # batched: gradient lives on the sorted unique pattern
+    grad_indices: Optional[torch.Tensor]  # int64 (3, nnz_unique)
+    seg: Optional[torch.Tensor]  # (nnz_unique + 1) run offsets into the sorted order when duplicates exist
+    sort_perm: Optional[torch.Tensor]  # sorted position -> storage position (for segment sums)
+    nnz_unique: int
+
+
+def _sort_coo(indices: torch.Tensor, dims, key_dims: int, perm_idx: int, want_sorted: bool):
+    """Run tsgu_coo_sort; returns (perm, sorted_indices or None)."""
+    dev = indices.device
+    ndim, nnz = indices.shape
+    perm = torch.empty(nnz, dtype=nat.IDX_TORCH[perm_idx], device=dev)
+    sorted_idx = torch.empty((ndim, nnz), dtype=torch.int64, device=dev) if want_sorted else None
+    if nnz == 0:
+        return perm, sorted_idx
+    L = nat.lib()
+    dims_c = (ctypes.c_int64 * 3)(*([int(d) for d in dims] + [1] * (3 - len(dims))))
+    with torch.cuda.device(dev):
+        ws = nat.workspace(L.tsgu_coo_sort_workspace_bytes(ndim, nnz, perm_idx), dev)
+        nat.check(L.tsgu_coo_sort(nat.ptr(indices), ndim, nnz, indices.stride(0), dims_c, key_dims,
+                                  nat.ptr(sorted_idx), nat.ptr(perm), perm_idx, nat.ptr(ws), ws.numel(),
+                                  nat.stream_ptr(dev)), "tsgu_coo_sort")
+    return perm, sorted_idx
+
+
+def _coo_to_flat_csr(indices: torch.Tensor, batch: int, n: int, m: int, perm: Optional[torch.Tensor], idx: int,
+                     keep=()) -> CsrPattern:
+    dev = indices.device
+    ndim, nnz = indices.shape
+    odt = nat.IDX_TORCH[idx]
+    rowptr = torch.empty(batch * n + 1, dtype=odt, device=dev)
+    colind = torch.empty(nnz, dtype=odt, device=dev)
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().tsgu_coo_to_csr(nat.ptr(indices), ndim, nnz, indices.stride(0), batch, n, nat.ptr(perm),
+                                            nat.ptr(rowptr), nat.ptr(colind), idx, nat.stream_ptr(dev)),
+                  "tsgu_coo_to_csr")
+    return CsrPattern(rowptr, colind, perm, batch, n, m, n, 0, nnz, idx, keep=keep)
+
+
+def coo_pattern(A: torch.Tensor) -> CooPattern:
+    """COO -> kernel-ready structure (sort + rowptr), cached per index tensor."""
+    ind = A._indices()
+    coalesced = A.is_coalesced()
+    key = ("coo", ind.data_ptr(), ind._version, tuple(A.shape), coalesced, ind.device)
+    hit = _cache_get(key)
+    if hit is not None:
+        return hit
+    if ind.stride(1) != 1:
+        ind = ind.contiguous()
+    batched = A.dim() == 3
+    batch = A.shape[0] if batched else 1
+    n, m = A.shape[-2], A.shape[-1]
+    nnz = ind.shape[1]
+    idx = _internal_idx(batch, n, m, nnz)
+    if not batched:
+        if coalesced:  # already sorted and unique: no sort, identity value map
+            csr = _coo_to_flat_csr(ind, 1, n, m, None, idx, keep=(ind,))
+            pat = CooPattern(csr, None, None, None, None, nnz)
+        else:  # stable sort by row only: entries of a row keep storage order, duplicates just add up
+            perm, _ = _sort_coo(ind, (n, m), 1, idx, False)
+            csr = _coo_to_flat_csr(ind, 1, n, m, perm, idx, keep=(ind,))
+            pat = CooPattern(csr, perm, None, None, None, nnz)
+    else:
+        dims = (batch, n, m)
+        if coalesced:
+            csr = _coo_to_flat_csr(ind, batch, n, m, None, idx, keep=(ind,))
+            pat = CooPattern(csr, None, ind, None, None, nnz)
+        else:
+            perm, srt = _sort_coo(ind, dims, 3, idx, True)
+            dup = False
+            if nnz > 1:
+                first = torch.ones(nnz, dtype=torch.bool, device=ind.device)
+                first[1:] = (srt[:, 1:] != srt[:, :-1]).any(dim=0)
+                dup = not bool(first.all())  # one-off host sync per pattern (sizes the gradient)
+            if not dup:
+                csr = _coo_to_flat_csr(ind, batch, n, m, perm, idx, keep=(ind,))
+                pat = CooPattern(csr, None, srt, None, perm, nnz)
+            else:
+                # the reference coalesces every item before multiplying (utils/utils.py:580), so both
+                # the product and the gradient live on the sorted unique pattern
+                uniq = srt[:, first].contiguous()
+                starts = torch.nonzero(first).flatten()
+                seg = torch.cat([starts, starts.new_tensor([nnz])]).to(nat.IDX_TORCH[idx])
+                csr = _coo_to_flat_csr(uniq, batch, n, m, None, idx, keep=(ind,))
+                pat = CooPattern(csr, None, uniq, seg, perm, uniq.shape[1])
+    _cache_put(key, pat)
+    return pat

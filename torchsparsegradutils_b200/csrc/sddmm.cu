@@ -1,0 +1,273 @@
+// sddmm.cu -- fused SDDMM for sm_100a:  out[e] = < G[r_e, :], B[c_e, :] >.
+//
+// Replaces the reference's un-fused grad_A (sparse_matmul.py:190-205): repeat_interleave row
+// expansion + 2x index_select + mul + sum, which materialise 3 nnz x K temporaries.  Here the row
+// index is implied by the row-split (never materialised), G[r,:] is held in registers for the whole
+// row, each B row is read once with 128-bit loads, and the NB per-entry partial dot products that a
+// group of LPR lanes holds are reduced with a halving butterfly: (NB-1) + log2(LPR/NB) shuffles per
+// NB entries instead of NB*log2(LPR).
+#include "common.cuh"
+
+namespace tsgu {
+
+template <typename V, typename I>
+struct SddmmParams {
+  const I* rowptr;
+  const I* colind;
+  const I* out_index;  // nullable
+  const V* G;
+  const V* B;
+  V* out;
+  int64_t batch, n, K;
+  int64_t rowptr_bstride, nnz_bstride;
+  int64_t g_bs, g_rs, g_cs, b_bs, b_rs, b_cs;
+};
+
+// Reduce NB per-lane partials across the LPR lanes of a group.  On return lane gl holds in p[0] the
+// total of entry (gl / (LPR/NB)).
+template <typename Acc, int LPR, int NB>
+__device__ __forceinline__ void butterfly_reduce(Acc (&p)[NB], unsigned gmask, int gl) {
+  static_assert(NB <= LPR, "NB entries need NB lanes to land on");
+  int width = NB;
+#pragma unroll
+  for (int s = LPR / 2; s >= 1; s >>= 1) {
+    if (width > 1) {
+      const int half = width / 2;
+      const bool upper = (gl & s) != 0;
+#pragma unroll
+      for (int i = 0; i < NB / 2; ++i) {
+        if (i < half) {
+          const Acc send = upper ? p[i] : p[i + half];
+          const Acc keep = upper ? p[i + half] : p[i];
+          p[i] = keep + shfl_x(gmask, send, s);
+        }
+      }
+      width = half;
+    } else {
+      p[0] += shfl_x(gmask, p[0], s);
+    }
+  }
+}
+
+template <typename V, typename I, int EPV, int LPR, int VPL, int NB>
+__global__ void __launch_bounds__(256) sddmm_rowsplit_kernel(const SddmmParams<V, I> p) {
+  using Acc = typename VT<V>::Acc;
+  static_assert(EPV == 1 || EPV * sizeof(V) == 16, "vector path is 128-bit");
+  constexpr int CHUNK = LPR * VPL * EPV;
+  constexpr int LPE = LPR / NB;  // lanes that end up holding the same entry
+
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR;
+  const unsigned gmask = group_mask<LPR>(lane);
+  const int64_t groups_per_block = blockDim.x / LPR;
+  const int64_t total_rows = p.batch * p.n;
+  const bool single_chunk = p.K <= CHUNK;
+
+  for (int64_t r = (int64_t)blockIdx.x * groups_per_block + threadIdx.x / LPR; r < total_rows;
+       r += (int64_t)gridDim.x * groups_per_block) {
+    const int64_t item = (p.batch == 1) ? 0 : r / p.n;
+    const int64_t lr = r - item * p.n;
+    const I* rp = p.rowptr + item * p.rowptr_bstride + lr;
+    const int64_t e0 = (int64_t)__ldg(rp) + item * p.nnz_bstride;
+    const int64_t e1 = (int64_t)__ldg(rp + 1) + item * p.nnz_bstride;
+    if (e0 >= e1) continue;
+    const V* Bi = p.B + item * p.b_bs;
+    const V* Grow = p.G + item * p.g_bs + lr * p.g_rs;
+
+    Acc g[VPL][EPV];
+    auto load_g = [&](int64_t k0) {
+#pragma unroll
+      for (int w = 0; w < VPL; ++w) {
+        const int64_t kk = k0 + (int64_t)(w * LPR + gl) * EPV;
+        Raw<V, EPV> raw = (kk < p.K) ? raw_ldg<V, EPV>(Grow + (EPV == 1 ? kk * p.g_cs : kk)) : raw_zero<V, EPV>();
+        raw_unpack<V, EPV>(raw, g[w]);
+      }
+    };
+    if (single_chunk) load_g(0);
+
+    for (int64_t base = e0; base < e1; base += NB) {
+      const int64_t e = base + gl;
+      I c = (gl < NB && e < e1) ? __ldg(p.colind + e) : I(0);
+      const int cnt = (int)min((int64_t)NB, e1 - base);
+      Acc part[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) part[j] = Acc(0);
+
+      for (int64_t k0 = 0; k0 < p.K; k0 += CHUNK) {
+        if (!single_chunk) load_g(k0);
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const int64_t cj = (int64_t)shfl_idx(gmask, c, j, LPR);
+          const V* brow = Bi + cj * p.b_rs;
+          Raw<V, EPV> b[VPL];
+#pragma unroll
+          for (int w = 0; w < VPL; ++w) {
+            const int64_t kk = k0 + (int64_t)(w * LPR + gl) * EPV;
+            b[w] = (j < cnt && kk < p.K) ? raw_ldg<V, EPV>(brow + (EPV == 1 ? kk * p.b_cs : kk))
+                                          : raw_zero<V, EPV>();
+          }
+#pragma unroll
+          for (int w = 0; w < VPL; ++w) {
+            Acc x[EPV];
+            raw_unpack<V, EPV>(b[w], x);
+#pragma unroll
+            for (int i = 0; i < EPV; ++i) part[j] = fma(g[w][i], x[i], part[j]);
+          }
+        }
+      }
+      butterfly_reduce<Acc, LPR, NB>(part, gmask, gl);
+      const int slot = gl / LPE;
+      if ((gl % LPE) == 0 && slot < cnt) {
+        const int64_t eo = base + slot;
+        int64_t dst = eo;
+        if (p.out_index) dst = (int64_t)__ldg(p.out_index + eo);
+        if (dst >= 0) p.out[dst] = VT<V>::from_acc(part[0]);
+      }
+    }
+  }
+}
+
+template <typename V, typename I, int EPV, int LPR, int VPL>
+static int launch_sddmm(const SddmmParams<V, I>& p, cudaStream_t s) {
+  constexpr int NB = LPR < 16 ? LPR : 16;
+  const int threads = 256;
+  const int64_t gpb = threads / LPR;
+  int64_t blocks = (p.batch * p.n + gpb - 1) / gpb;
+  if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;
+  sddmm_rowsplit_kernel<V, I, EPV, LPR, VPL, NB><<<(unsigned)blocks, threads, 0, s>>>(p);
+  count_launch();
+  return launch_status();
+}
+
+template <typename V, typename I>
+static int sddmm_dispatch(const SddmmParams<V, I>& p, cudaStream_t s) {
+  constexpr int EPVF = 16 / sizeof(V);
+  const bool vec_ok = p.b_cs == 1 && p.g_cs == 1 && (p.K % EPVF) == 0 && (p.b_rs % EPVF) == 0 &&
+                      (p.b_bs % EPVF) == 0 && (p.g_rs % EPVF) == 0 && (p.g_bs % EPVF) == 0 &&
+                      aligned16(p.B) && aligned16(p.G);
+  if (vec_ok) {
+    const int64_t kv = p.K / EPVF;
+    if (kv <= 4) return launch_sddmm<V, I, EPVF, 4, 1>(p, s);
+    if (kv <= 8) return launch_sddmm<V, I, EPVF, 8, 1>(p, s);
+    if (kv <= 16) return launch_sddmm<V, I, EPVF, 16, 1>(p, s);
+    if (kv <= 32) return launch_sddmm<V, I, EPVF, 32, 1>(p, s);
+    if (kv <= 64) return launch_sddmm<V, I, EPVF, 32, 2>(p, s);
+    return launch_sddmm<V, I, EPVF, 32, 4>(p, s);
+  }
+  if (p.K == 1) return launch_sddmm<V, I, 1, 1, 1>(p, s);
+  if (p.K <= 4) return launch_sddmm<V, I, 1, 4, 1>(p, s);
+  return launch_sddmm<V, I, 1, 32, 1>(p, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// COO variant: entries are independent; a group of LPR lanes handles NB consecutive entries.
+// ---------------------------------------------------------------------------------------------
+template <typename V, int EPV, int LPR, int NB>
+__global__ void __launch_bounds__(256) sddmm_coo_kernel(const int64_t* __restrict__ row,
+                                                        const int64_t* __restrict__ col,
+                                                        const V* __restrict__ G, const V* __restrict__ B,
+                                                        V* __restrict__ out, int64_t nnz, int64_t K,
+                                                        int64_t g_rs, int64_t g_cs, int64_t b_rs, int64_t b_cs) {
+  using Acc = typename VT<V>::Acc;
+  constexpr int CHUNK = LPR * EPV;
+  constexpr int LPE = LPR / NB;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR;
+  const unsigned gmask = group_mask<LPR>(lane);
+  const int64_t groups_per_block = blockDim.x / LPR;
+  const int64_t ngroups = (nnz + NB - 1) / NB;
+  for (int64_t grp = (int64_t)blockIdx.x * groups_per_block + threadIdx.x / LPR; grp < ngroups;
+       grp += (int64_t)gridDim.x * groups_per_block) {
+    const int64_t base = grp * NB;
+    const int64_t e = base + gl;
+    const bool ok = gl < NB && e < nnz;
+    int64_t r = ok ? __ldg(row + e) : 0;
+    int64_t c = ok ? __ldg(col + e) : 0;
+    const int cnt = (int)min((int64_t)NB, nnz - base);
+    Acc part[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) part[j] = Acc(0);
+    for (int64_t k0 = 0; k0 < K; k0 += CHUNK) {
+      const int64_t kk = k0 + (int64_t)gl * EPV;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int64_t rj = shfl_idx(gmask, r, j, LPR);
+        const int64_t cj = shfl_idx(gmask, c, j, LPR);
+        Raw<V, EPV> gr = raw_zero<V, EPV>(), br = raw_zero<V, EPV>();
+        if (j < cnt && kk < K) {
+          gr = raw_ldg<V, EPV>(G + rj * g_rs + (EPV == 1 ? kk * g_cs : kk));
+          br = raw_ldg<V, EPV>(B + cj * b_rs + (EPV == 1 ? kk * b_cs : kk));
+        }
+        Acc x[EPV], y[EPV];
+        raw_unpack<V, EPV>(gr, x);
+        raw_unpack<V, EPV>(br, y);
+#pragma unroll
+        for (int i = 0; i < EPV; ++i) part[j] = fma(x[i], y[i], part[j]);
+      }
+    }
+    butterfly_reduce<Acc, LPR, NB>(part, gmask, gl);
+    const int slot = gl / LPE;
+    if ((gl % LPE) == 0 && slot < cnt) out[base + slot] = VT<V>::from_acc(part[0]);
+  }
+}
+
+template <typename V, int EPV, int LPR>
+static int launch_sddmm_coo(const int64_t* row, const int64_t* col, const V* G, const V* B, V* out,
+                            int64_t nnz, int64_t K, int64_t g_rs, int64_t g_cs, int64_t b_rs,
+                            int64_t b_cs, cudaStream_t s) {
+  constexpr int NB = LPR < 8 ? LPR : 8;
+  const int threads = 256;
+  const int64_t gpb = threads / LPR;
+  const int64_t ngroups = (nnz + NB - 1) / NB;
+  int64_t blocks = (ngroups + gpb - 1) / gpb;
+  if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;
+  sddmm_coo_kernel<V, EPV, LPR, NB><<<(unsigned)blocks, threads, 0, s>>>(row, col, G, B, out, nnz, K, g_rs,
+                                                                        g_cs, b_rs, b_cs);
+  count_launch();
+  return launch_status();
+}
+
+}  // namespace tsgu
+
+extern "C" int tsgu_sddmm_csr(const void* rowptr, const void* colind, const void* out_index, const void* G,
+                              const void* B, void* out, int64_t batch, int64_t n, int64_t m, int64_t K,
+                              int64_t rowptr_bstride, int64_t nnz_bstride, int64_t nnz_total, int64_t g_bs,
+                              int64_t g_rs, int64_t g_cs, int64_t b_bs, int64_t b_rs, int64_t b_cs,
+                              int val_dtype, int idx_dtype, int algo, void* stream) {
+  (void)m;
+  if (batch < 0 || n < 0 || K < 0) return TSGU_ERR_SHAPE;
+  if (algo != TSGU_ALGO_AUTO && algo != TSGU_ALGO_ROWSPLIT && algo != TSGU_ALGO_MERGE) return TSGU_ERR_ALGO;
+  if (batch == 0 || n == 0 || nnz_total == 0) return 0;
+  TSGU_DISPATCH_VAL(val_dtype, TSGU_DISPATCH_IDX(idx_dtype, {
+    tsgu::SddmmParams<V, I> p;
+    p.rowptr = (const I*)rowptr; p.colind = (const I*)colind; p.out_index = (const I*)out_index;
+    p.G = (const V*)G; p.B = (const V*)B; p.out = (V*)out;
+    p.batch = batch; p.n = n; p.K = K;
+    p.rowptr_bstride = rowptr_bstride; p.nnz_bstride = nnz_bstride;
+    p.g_bs = g_bs; p.g_rs = g_rs; p.g_cs = g_cs; p.b_bs = b_bs; p.b_rs = b_rs; p.b_cs = b_cs;
+    return tsgu::sddmm_dispatch<V, I>(p, tsgu::as_stream(stream));
+  }));
+  return 0;
+}
+
+extern "C" int tsgu_sddmm_coo(const int64_t* row, const int64_t* col, const void* G, const void* B, void* out,
+                              int64_t nnz, int64_t K, int64_t g_rs, int64_t g_cs, int64_t b_rs, int64_t b_cs,
+                              int val_dtype, void* stream) {
+  if (nnz < 0 || K < 0) return TSGU_ERR_SHAPE;
+  if (nnz == 0) return 0;
+  cudaStream_t s = tsgu::as_stream(stream);
+  TSGU_DISPATCH_VAL(val_dtype, {
+    constexpr int EPVF = 16 / sizeof(V);
+    const V* g = (const V*)G; const V* b = (const V*)B; V* o = (V*)out;
+    const bool vec_ok = g_cs == 1 && b_cs == 1 && (K % EPVF) == 0 && (g_rs % EPVF) == 0 && (b_rs % EPVF) == 0 &&
+                        tsgu::aligned16(G) && tsgu::aligned16(B);
+    if (vec_ok) {
+      const int64_t kv = K / EPVF;
+      if (kv <= 8) return tsgu::launch_sddmm_coo<V, EPVF, 8>(row, col, g, b, o, nnz, K, g_rs, g_cs, b_rs, b_cs, s);
+      return tsgu::launch_sddmm_coo<V, EPVF, 32>(row, col, g, b, o, nnz, K, g_rs, g_cs, b_rs, b_cs, s);
+    }
+    if (K <= 4) return tsgu::launch_sddmm_coo<V, 1, 4>(row, col, g, b, o, nnz, K, g_rs, g_cs, b_rs, b_cs, s);
+    return tsgu::launch_sddmm_coo<V, 1, 32>(row, col, g, b, o, nnz, K, g_rs, g_cs, b_rs, b_cs, s);
+  });
+  return 0;
+}
