@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- sparse_mm forward+backward throughput on B200 (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2] [--impl reference]
+
+One step = one forward + backward of ``sparse_mm(A, B)`` (C = A B; grad_A by SDDMM; grad_B = A^T G)
+over one batch of synthetic input.  Default workload = BASELINE.json configs[1] ("config 2"): batched
+CSR, batch 8, 65536 x 65536, 16 nnz/row, dense 65536 x 128, fp32 / int32.  With N > 1 (launched by
+torchrun, one rank per GPU) the 8 batch items are sharded across the ranks -- independent items, no
+data-path collective (strong scaling: total work fixed).
+
+Prints ONE JSON line (rank 0).  `value` = nnz/s with inputs resident in HBM; `e2e` = the same metric
+through the public API from pinned HOST buffers (H2D of A, B, G and D2H of C, grad_A, grad_B inside
+the timed region); `roofline` = the dominant kernel against the measured HBM copy bandwidth;
+`cpu_baseline` = the reference's CPU data flow (oracle/reference_port.py) on this host's cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import workloads as W  # noqa: E402
+
+METRIC, UNIT = "sparse_mm_fwd_bwd_nnz_per_s", "nnz/s"
+
+CONFIGS = {
+    # name: (builder kwargs) -- see workloads.py / SURVEY.md section 8(d)
+    "1": dict(kind="coo", n=4096, m=4096, nnz=167772, K=64, dtype="f32", batch=None,
+              desc="COO 4096x4096 @1% x dense 4096x64 fp32 (BASELINE configs[0])"),
+    "2": dict(kind="csr_uniform", n=65536, m=65536, per_row=16, K=128, dtype="f32", batch=8,
+              desc="batched CSR b=8 65536x65536 16 nnz/row x dense 65536x128 fp32 int32 (BASELINE configs[1])"),
+    "3": dict(kind="stencil", D=128, K=32, dtype="f32", batch=None,
+              desc="27-point 128^3 stencil CSR (55.7M nnz) x dense 2097152x32 fp32 (BASELINE configs[2])"),
+    "4": dict(kind="rmat", scale=22, K=128, dtype="bf16", batch=None,
+              desc="R-MAT 2^22 rows ~64M nnz x dense 2^22x128 bf16 (BASELINE configs[3])"),
+    "5": dict(kind="csr_uniform", n=262144, m=262144, per_row=8, K=512, dtype="f32", batch=None,
+              desc="CSR 262144^2 8 nnz/row x dense 262144x512 fp32 (BASELINE configs[4])"),
+    "5bf16": dict(kind="csr_uniform", n=262144, m=262144, per_row=8, K=512, dtype="bf16", batch=None,
+                  desc="CSR 262144^2 8 nnz/row x dense 262144x512 bf16 (BASELINE configs[4])"),
+}
+DT = {"f32": torch.float32, "f64": torch.float64, "bf16": torch.bfloat16}
+
+
+def build_inputs(cfg, device, batch_slice=None, seed_shift=0):
+    """Returns (A, B, G) on `device`.  batch_slice=(lo, hi) keeps only those batch items (rank shard /
+    CPU sample); the full batch is generated with the fixed seed first so shards see identical data."""
+    dt = DT[cfg["dtype"]]
+    if cfg["kind"] == "coo":
+        A = W.uniform_coo(cfg["n"], cfg["m"], cfg["nnz"], dt, device, seed=1 + seed_shift)
+    elif cfg["kind"] == "csr_uniform":
+        A = W.uniform_rows_csr(cfg["batch"], cfg["n"], cfg["m"], cfg["per_row"], dt, torch.int32, device,
+                               seed=2 + seed_shift)
+    elif cfg["kind"] == "stencil":
+        A = W.stencil27_csr(cfg["D"], dt, torch.int32, device, seed=3 + seed_shift)
+    elif cfg["kind"] == "rmat":
+        A = W.rmat_csr(cfg["scale"], 16, dt, torch.int32, device, seed=4 + seed_shift)
+    else:
+        raise ValueError(cfg["kind"])
+    B, G = W.dense_operands(tuple(A.shape), cfg["K"], dt, device, seed=100 + seed_shift)
+    if batch_slice is not None and A.dim() == 3:
+        lo, hi = batch_slice
+        A = torch.sparse_csr_tensor(A.crow_indices()[lo:hi].contiguous(), A.col_indices()[lo:hi].contiguous(),
+                                    A.values()[lo:hi].contiguous(), (hi - lo,) + tuple(A.shape[1:]))
+        B, G = B[lo:hi].contiguous(), G[lo:hi].contiguous()
+    return A, B, G
+
+
+def problem_stats(A, K):
+    batch = A.shape[0] if A.dim() == 3 else 1
+    n, m = A.shape[-2], A.shape[-1]
+    nnz_total = A._nnz() * batch if (A.layout == torch.sparse_csr and A.dim() == 3) else A._nnz()
+    s_v = A.dtype.itemsize
+    coo = A.layout == torch.sparse_coo
+    s_i = 8 if coo else A.crow_indices().dtype.itemsize
+    alg = W.algorithmic_bytes(batch, n, m, nnz_total // batch, K, s_v, s_i, coo=coo)
+    return dict(batch=batch, n=n, m=m, nnz=nnz_total, K=K, s_v=s_v, s_i=s_i, alg=alg,
+                flops=6 * nnz_total * K, gather_bytes_per_pass=nnz_total * K * s_v)
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    """Samples SM clock / throttle reasons DURING the timed region (NVML, ~20 ms period)."""
+
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+    NOTE = {"sw_power_cap": 0x4, "hw_power_brake": 0x80}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # honour CUDA_VISIBLE_DEVICES by resolving through the CUDA device's UUID
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for name, bit in {**self.BAD, **self.NOTE}.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def report(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------ CPU baseline
+def cpu_reference_run(cfg, steps, warmup, sample_note_only=False):
+    """Time the reference's CPU data flow (torch CPU ops, all host threads) on a bounded sample of the
+    workload: one batch item for batched configs, a row prefix for the very large single matrices."""
+    from oracle import reference_port as rp
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    c = dict(cfg)
+    sample = "full workload"
+    if c.get("batch"):
+        c["batch"] = 1
+        sample = f"1 of {cfg['batch']} batch items (same n, nnz/row, K)"
+    if c["kind"] == "stencil":
+        c["D"] = 64
+        sample = "64^3 volume (1/8 of the rows, same stencil)"
+    if c["kind"] == "rmat":
+        c["scale"] = 18
+        sample = "R-MAT scale 18 (1/16 of the rows, same edge factor)"
+    if c["dtype"] == "bf16":
+        c["dtype"] = "f32"
+        sample += "; fp32 (the reference's CPU CSR path has no bf16)"
+    A, B, G = build_inputs(c, "cpu")
+    nnz = problem_stats(A, c["K"])["nnz"]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        rp.forward_backward(A, B, G)
+        times.append(time.perf_counter() - t0)
+    times = times[warmup:]
+    sec = statistics.median(times)
+    return dict(value=nnz / sec, unit=UNIT, cores=torch.get_num_threads(), kind="port", sample=sample,
+                ms_per_step=sec * 1e3, nnz_per_step=nnz, steps=len(times))
+
+
+# ------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", default="2", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(args.warmup, 3)
+    config_out = {"workload": cfg["desc"], "config_id": args.config, "K": cfg["K"],
+                  "l2": "inputs larger than L2 (B+G+C+gradB = 4 x 256 MiB per step >> 126 MB); no explicit flush",
+                  "sharding": f"batch items split over {world} rank(s), no collective" if cfg.get("batch") else "replicas"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        base = cpu_reference_run(cfg, steps=max(1, min(args.steps, 3)), warmup=1)
+        line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": base["steps"], "warmup": 1, "ms_per_step": base["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_out,
+                "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------------- B200 arm
+    from torchsparsegradutils_b200 import _native as nat
+    from torchsparsegradutils_b200 import _ops, sparse_mm
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    if cfg.get("batch") and world > 1:
+        assert cfg["batch"] % world == 0, "batch must divide across ranks"
+        per = cfg["batch"] // world
+        shard = (rank * per, (rank + 1) * per)
+    else:
+        shard = None
+    A, B, G = build_inputs(cfg, dev, shard)
+    st = problem_stats(A, cfg["K"])
+    A.requires_grad_(True)
+    B.requires_grad_(True)
+
+    def step():
+        A.grad = None
+        B.grad = None
+        C = sparse_mm(A, B)
+        C.backward(G)
+        return C
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    launches0 = nat.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk, _ops.KernelTimer() as kt:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = nat.launch_count() - launches0
+    if dist is not None:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t)
+        cnt = torch.tensor([st["nnz"], launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(cnt)
+        nnz_all, launches_all = int(cnt[0]), int(cnt[1])
+    else:
+        nnz_all, launches_all = st["nnz"], launches
+    ms_step = ms_total / args.steps
+    value = nnz_all / (ms_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (live CUDA-event durations from the timed region)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    ksum = kt.summary()
+    kernels = {}
+    for tag, rec in ksum.items():
+        alg = st["alg"].get(tag)
+        if alg is None:
+            continue
+        gbs = alg / (rec["ms"] * 1e-3) / 1e9
+        kernels[tag] = {"ms": rec["ms"], "launches": rec["launches"], "alg_bytes": alg, "achieved_gbs": gbs,
+                        "frac": gbs / peak, "gather_gbs": st["gather_bytes_per_pass"] / (rec["ms"] * 1e-3) / 1e9}
+    dom = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
+    roofline = None
+    if dom:
+        d = kernels[dom]
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": d["frac"], "traffic": None, "peak_source": peak_src,
+                    "share_of_step": d["ms"] / ms_step, "l2_gather_gbs": d["gather_gbs"]}
+    step_gbs = st["alg"]["total"] / (ms_step * 1e-3) / 1e9
+
+    # ---- e2e: same step through the public API from pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(A.detach(), B.detach(), G, args.e2e_steps, dev, dist, sparse_mm)
+        e2e["value"] = (nnz_all / (e2e.pop("ms_per_step_max") * 1e-3))
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cpu_reference_run(cfg, steps=5, warmup=1)
+        cpu_base = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if cfg.get("batch") else "weak",
+                "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic", "config": config_out,
+                "clocks": clk.report(), "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline,
+                "cpu_baseline": cpu_base, "gflops": st["flops"] * (nnz_all / st["nnz"]) / (ms_step * 1e-3) / 1e9,
+                "step_alg_gbs": step_gbs * (nnz_all / st["nnz"]), "step_frac_of_hbm_peak": step_gbs / peak,
+                "kernels": kernels, "nnz_per_step": nnz_all}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_e2e(A, B, G, steps, dev, dist, sparse_mm):
+    """Public-API step from HOST memory: pinned H2D of (crow, col, values | indices, values), B, G; the
+    op; D2H of C, grad_A values and grad_B into pinned buffers.  Everything inside the timed region."""
+    pin = lambda t: t.detach().cpu().pin_memory()  # noqa: E731
+    if A.layout == torch.sparse_csr:
+        hA = [pin(A.crow_indices()), pin(A.col_indices()), pin(A.values())]
+    else:
+        hA = [pin(A._indices()), pin(A._values())]
+    hB, hG = pin(B), pin(G)
+    shape = tuple(A.shape)
+    is_csr = A.layout == torch.sparse_csr
+    outC = torch.empty(tuple(G.shape), dtype=G.dtype).pin_memory()
+    outgB = torch.empty(tuple(B.shape), dtype=B.dtype).pin_memory()
+    outgA = torch.empty(hA[-1].shape, dtype=hA[-1].dtype).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in hA + [hB, hG])
+    d2h = sum(t.numel() * t.element_size() for t in (outC, outgB, outgA))
+
+    def one():
+        dA = [t.to(dev, non_blocking=True) for t in hA]
+        dB = hB.to(dev, non_blocking=True).requires_grad_(True)
+        dG = hG.to(dev, non_blocking=True)
+        if is_csr:
+            As = torch.sparse_csr_tensor(dA[0], dA[1], dA[2], shape).requires_grad_(True)
+        else:
+            As = torch.sparse_coo_tensor(dA[0], dA[1], shape, is_coalesced=True).requires_grad_(True)
+        C = sparse_mm(As, dB)
+        C.backward(dG)
+        outC.copy_(C.detach(), non_blocking=True)
+        outgB.copy_(dB.grad, non_blocking=True)
+        gv = As.grad.values() if is_csr else As.grad._values()
+        outgA.copy_(gv.reshape(outgA.shape), non_blocking=True)
+
+    for _ in range(2):
+        one()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3 / steps
+    ms = e0.elapsed_time(e1) / steps
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    return {"value": None, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms,
+            "ms_per_step_max": ms, "wall_ms_per_step": wall_ms, "steps": steps,
+            "note": "pattern cache cold every step (fresh device index tensors): includes the CSR transpose build"}
+
+
+if __name__ == "__main__":
+    main()

@@ -75,3 +75,25 @@ def test_index_builders_bit_exact(name):
             assert np.array_equal(rT, g(f"T_crow_{it}"))
             assert np.array_equal(cT, g(f"T_col_{it}"))
             assert np.array_equal(pT, g(f"T_perm_{it}"))
+
+
+@pytest.mark.parametrize("name", MM_CASES)
+def test_reference_port_matches_golden(name):
+    """The torch-CPU port used for the CPU baseline issues the reference's ATen calls: same numbers."""
+    import torch
+
+    from oracle import reference_port as rp
+
+    g = lambda k: GOLDEN[f"{name}/{k}"]  # noqa: E731
+    shape = tuple(int(x) for x in g("shape"))
+    vals = torch.from_numpy(g("values"))
+    if str(g("layout")) == "coo":
+        A = torch.sparse_coo_tensor(torch.from_numpy(g("indices")), vals, shape)
+    else:
+        A = torch.sparse_csr_tensor(torch.from_numpy(g("crow")), torch.from_numpy(g("col")), vals, shape)
+    B = torch.from_numpy(strided(g("B"), g("B_strides")))
+    C, gA, gB = rp.forward_backward(A, B, torch.from_numpy(g("G")))
+    t = tol(g("B").dtype)
+    np.testing.assert_allclose(C.numpy(), g("C"), **t)
+    np.testing.assert_allclose(gB.numpy(), g("gradB"), **t)
+    np.testing.assert_allclose(gA.numpy().reshape(g("gradA_values").shape), g("gradA_values"), **t)

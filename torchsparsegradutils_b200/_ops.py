@@ -11,6 +11,51 @@ from ._pattern import CsrPattern
 _VEC_ELEMS = {torch.float32: 4, torch.float64: 2, torch.bfloat16: 8}
 
 
+class KernelTimer:
+    """Optional per-kernel CUDA-event timing on the launching stream (bench.py's roofline numbers).
+
+    ``with KernelTimer() as kt: ...`` brackets every SpMM / SDDMM launch issued by this module with
+    events; ``kt.summary()`` (after a synchronize) gives mean milliseconds and launch count per kernel
+    tag.  Inactive by default: the hot path then records nothing.
+    """
+
+    active = None
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        KernelTimer.active = self
+        return self
+
+    def __exit__(self, *exc):
+        KernelTimer.active = None
+
+    def summary(self):
+        out = {}
+        for tag, e0, e1 in self.records:
+            ms, cnt = out.get(tag, (0.0, 0))
+            out[tag] = (ms + e0.elapsed_time(e1), cnt + 1)
+        return {k: {"ms": v[0] / v[1], "launches": v[1]} for k, v in out.items()}
+
+
+class _timed:
+    def __init__(self, tag, device):
+        self.kt = KernelTimer.active
+        self.tag, self.device = tag, device
+
+    def __enter__(self):
+        if self.kt is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream(self.device))
+
+    def __exit__(self, *exc):
+        if self.kt is not None:
+            self.e1.record(torch.cuda.current_stream(self.device))
+            self.kt.records.append((self.tag, self.e0, self.e1))
+
+
 def _vector_ready(x: torch.Tensor) -> bool:
     """Can the 128-bit kernels read this (batch, rows, K) operand in place?"""
     epv = _VEC_ELEMS[x.dtype]
@@ -58,7 +103,8 @@ def _strides(x: torch.Tensor):
     return (bs if x.shape[0] > 1 else 0, rs if x.shape[1] > 1 else 0, cs if x.shape[2] > 1 else 1)
 
 
-def spmm(pat: CsrPattern, vals: torch.Tensor, dense: torch.Tensor, algo: int = nat.ALGO_AUTO) -> torch.Tensor:
+def spmm(pat: CsrPattern, vals: torch.Tensor, dense: torch.Tensor, algo: int = nat.ALGO_AUTO,
+         tag: str = "spmm") -> torch.Tensor:
     """out[t] = A[t] @ dense[t]; dense is (batch, m, K) (any strides); returns contiguous (batch, n, K)."""
     dense = prepare_dense(_as3d(dense))
     K = dense.shape[-1]
@@ -68,7 +114,7 @@ def spmm(pat: CsrPattern, vals: torch.Tensor, dense: torch.Tensor, algo: int = n
     dev = dense.device
     L = nat.lib()
     vdt = nat.val_enum(dense.dtype)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _timed(tag, dev):
         ws_bytes = L.tsgu_spmm_workspace_bytes(pat.batch, pat.n, K, pat.nnz_total, vdt, algo)
         ws = nat.workspace(ws_bytes, dev) if ws_bytes else None
         nat.check(L.tsgu_spmm_csr(nat.ptr(pat.rowptr), nat.ptr(pat.colind), nat.ptr(vals), nat.ptr(pat.perm),
@@ -89,7 +135,7 @@ def sddmm(pat: CsrPattern, G: torch.Tensor, B: torch.Tensor, out_index: Optional
     if nnz_out == 0:
         return out
     dev = B.device
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _timed("sddmm", dev):
         nat.check(nat.lib().tsgu_sddmm_csr(nat.ptr(pat.rowptr), nat.ptr(pat.colind), nat.ptr(out_index),
                                            G.data_ptr(), B.data_ptr(), out.data_ptr(), pat.batch, pat.n, pat.m,
                                            B.shape[-1], pat.rowptr_bstride, pat.nnz_bstride, pat.nnz_total,

@@ -105,7 +105,7 @@ class SparseMatMul(torch.autograd.Function):
                 coalesced_vals = _ops.segment_sum_values(vals, pat.sort_perm, pat.seg, pat.nnz_unique)
                 vals = coalesced_vals
 
-        x = _ops.spmm(csr, vals, B)
+        x = _ops.spmm(csr, vals, B, tag="spmm_fwd")
         x = x if ctx.batched else x[0]
 
         ctx.pattern = pat
@@ -145,7 +145,7 @@ class SparseMatMul(torch.autograd.Function):
                 vals = A.values().contiguous()
             else:
                 vals = A._values().contiguous()
-            gradB = _ops.spmm(csr.transpose(), vals, grad)
+            gradB = _ops.spmm(csr.transpose(), vals, grad, tag="spmm_gradB")
             gradB = gradB if ctx.batched else gradB[0]
 
         return gradA, gradB
