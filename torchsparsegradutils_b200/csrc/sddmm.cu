@@ -7,6 +7,7 @@
 // group of LPR lanes holds are reduced with a halving butterfly: (NB-1) + log2(LPR/NB) shuffles per
 // NB entries instead of NB*log2(LPR).
 #include "common.cuh"
+#include "tile.cuh"
 
 namespace tsgu {
 
@@ -139,12 +140,185 @@ static int launch_sddmm(const SddmmParams<V, I>& p, cudaStream_t s) {
   return launch_status();
 }
 
+
+// =============================================================================================
+// Fast path: persistent row-tile kernel; rowptr / colind staged by the bulk-copy engine (tile.cuh).
+// =============================================================================================
+template <typename V, typename I, int LPR, int VPL, int NB, int U, bool EXACT>
+__global__ void __launch_bounds__(256, 3) sddmm_tile_kernel(const SddmmParams<V, I> p, const int64_t tiles_per_item,
+                                                            const int64_t num_tiles, const int64_t rowptr_len,
+                                                            const int64_t nnz_len) {
+  using Acc = typename VT<V>::Acc;
+  using Cfg = TileCfg<V, I, 0>;
+  using Smem = typename Cfg::Smem;
+  constexpr int EPV = 16 / sizeof(V);
+  constexpr int R = Cfg::TILE_ROWS, CAP = Cfg::CAP, AI = Cfg::ALN_I;
+  constexpr int LPE = LPR / NB;
+  static_assert(NB % U == 0, "batch is processed in chunks of U entries");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int gl = lane % LPR;
+  const unsigned gmask = group_mask<LPR>(lane);
+  const int group = tid / LPR;
+  constexpr int GROUPS = 256 / LPR;
+  const int kv = (int)(p.K / EPV);
+  const uint32_t row_bytes = (uint32_t)(p.b_rs * sizeof(V));
+  bool on[VPL];
+#pragma unroll
+  for (int w = 0; w < VPL; ++w) on[w] = EXACT || (w * LPR + gl < kv);
+
+  if (tid == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) mbar_init(&sm.full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  TileProducer<V, I, 0> prod{p.rowptr, p.colind, nullptr, nullptr, p.n, p.rowptr_bstride, p.nnz_bstride,
+                             tiles_per_item, rowptr_len, nnz_len};
+  int64_t nxt_s = 0, nxt_e = 0;
+  const int64_t t0 = blockIdx.x;
+  if (tid == 0 && t0 < num_tiles) {
+    int64_t s0, e0;
+    prod.bounds(t0, s0, e0);
+    prod.issue(sm.st[0], &sm.full[0], t0, s0, e0);
+    if (t0 + gridDim.x < num_tiles) prod.bounds(t0 + gridDim.x, nxt_s, nxt_e);
+  }
+
+  int it = 0;
+  for (int64_t t = t0; t < num_tiles; t += gridDim.x, ++it) {
+    const int stage = it & 1;
+    if (tid == 0) {
+      const int64_t tn = t + gridDim.x;
+      if (tn < num_tiles) {
+        prod.issue(sm.st[stage ^ 1], &sm.full[stage ^ 1], tn, nxt_s, nxt_e);
+        if (tn + gridDim.x < num_tiles) prod.bounds(tn + gridDim.x, nxt_s, nxt_e);
+      }
+    }
+    mbar_wait(&sm.full[stage], (uint32_t)((it >> 1) & 1));
+
+    const TileCoord c = tile_coord<R>(t, tiles_per_item, p.n);
+    const auto& st = sm.st[stage];
+    const int rp_shift = (int)((c.item * p.rowptr_bstride + c.r0) & (AI - 1));
+    const int64_t nnz_off = c.item * p.nnz_bstride;
+    const int64_t s_abs = (int64_t)st.rp[rp_shift] + nnz_off;
+    const int64_t e_abs = (int64_t)st.rp[rp_shift + c.rows] + nnz_off;
+    const bool staged = (e_abs - s_abs) <= CAP && e_abs > s_abs;
+    const I* scol = st.col + (int)(s_abs & (AI - 1));
+    const char* Bb = reinterpret_cast<const char*>(p.B + c.item * p.b_bs) + (size_t)gl * 16;
+
+    for (int lr = group; lr < c.rows; lr += GROUPS) {
+      const int64_t e0 = (int64_t)st.rp[rp_shift + lr] + nnz_off;
+      const int64_t e1 = (int64_t)st.rp[rp_shift + lr + 1] + nnz_off;
+      if (e0 >= e1) continue;
+      // the row of the upstream gradient stays in registers for the whole row of A
+      Acc g[VPL][EPV];
+      const V* Grow = p.G + c.item * p.g_bs + (c.r0 + lr) * p.g_rs;
+#pragma unroll
+      for (int w = 0; w < VPL; ++w) {
+        Raw<V, EPV> raw = (EXACT || on[w]) ? raw_ldg<V, EPV>(Grow + (int64_t)(w * LPR + gl) * EPV) : raw_zero<V, EPV>();
+        raw_unpack<V, EPV>(raw, g[w]);
+      }
+
+      for (int64_t base = e0; base < e1; base += NB) {
+        const int64_t e = base + gl;
+        uint32_t cu = 0;
+        if (gl < NB && e < e1) cu = staged ? (uint32_t)scol[(int)(e - s_abs)] : (uint32_t)__ldg(p.colind + e);
+        const int cnt = (int)min((int64_t)NB, e1 - base);
+        Acc part[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) part[j] = Acc(0);
+
+#pragma unroll
+        for (int j0 = 0; j0 < NB; j0 += U) {
+          if (j0 < cnt) {  // group-uniform
+            const bool full = (j0 + U <= cnt);
+            uint4 b[U][VPL];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const uint32_t cj = shfl_idx(gmask, cu, j0 + u, LPR);
+              const char* brow = Bb + (uint64_t)cj * row_bytes;
+#pragma unroll
+              for (int w = 0; w < VPL; ++w) {
+                if ((full || j0 + u < cnt) && (EXACT || on[w]))
+                  b[u][w] = __ldg(reinterpret_cast<const uint4*>(brow + w * (LPR * 16)));
+                else
+                  b[u][w] = make_uint4(0, 0, 0, 0);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+              for (int w = 0; w < VPL; ++w) {
+                Acc x[EPV];
+                Raw<V, EPV> raw;
+                raw.bits = b[u][w];
+                raw_unpack<V, EPV>(raw, x);
+#pragma unroll
+                for (int i = 0; i < EPV; ++i) part[j0 + u] = fma(g[w][i], x[i], part[j0 + u]);
+              }
+            }
+          }
+        }
+        butterfly_reduce<Acc, LPR, NB>(part, gmask, gl);
+        const int slot = gl / LPE;
+        if ((gl % LPE) == 0 && slot < cnt) {
+          const int64_t eo = base + slot;
+          int64_t dst = eo;
+          if (p.out_index) dst = (int64_t)__ldg(p.out_index + eo);
+          if (dst >= 0) p.out[dst] = VT<V>::from_acc(part[0]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename V, typename I, int LPR, int VPL>
+static int launch_sddmm_tile(const SddmmParams<V, I>& p, int64_t nnz_total, cudaStream_t s) {
+  using Cfg = TileCfg<V, I, 0>;
+  constexpr int NB = LPR < 16 ? LPR : 16;
+  constexpr int U0 = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
+  constexpr int U = U0 < NB ? U0 : NB;
+  constexpr int EPV = 16 / sizeof(V);
+  const bool exact = (p.K / EPV) == (int64_t)LPR * VPL;
+  auto kern = exact ? sddmm_tile_kernel<V, I, LPR, VPL, NB, U, true> : sddmm_tile_kernel<V, I, LPR, VPL, NB, U, false>;
+  const int smem = (int)sizeof(typename Cfg::Smem);
+  static_assert(sizeof(typename Cfg::Smem) <= 48 * 1024, "stay under the default dynamic smem limit");
+  static int ctas_per_sm[2] = {0, 0};
+  if (ctas_per_sm[exact] == 0) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem) != cudaSuccess || occ < 1) occ = 1;
+    ctas_per_sm[exact] = occ;
+  }
+  const int64_t tiles_per_item = (p.n + Cfg::TILE_ROWS - 1) / Cfg::TILE_ROWS;
+  const int64_t num_tiles = tiles_per_item * p.batch;
+  int64_t grid = (int64_t)kNumSMs * ctas_per_sm[exact];
+  if (grid > num_tiles) grid = num_tiles;
+  const int64_t rowptr_len = p.nnz_bstride > 0 ? p.batch * p.rowptr_bstride : p.batch * p.n + 1;
+  kern<<<(unsigned)grid, 256, smem, s>>>(p, tiles_per_item, num_tiles, rowptr_len, nnz_total);
+  count_launch();
+  return launch_status();
+}
+
 template <typename V, typename I>
-static int sddmm_dispatch(const SddmmParams<V, I>& p, cudaStream_t s) {
+static int sddmm_dispatch(const SddmmParams<V, I>& p, int64_t m, int64_t nnz_total, int algo, cudaStream_t s) {
   constexpr int EPVF = 16 / sizeof(V);
   const bool vec_ok = p.b_cs == 1 && p.g_cs == 1 && (p.K % EPVF) == 0 && (p.b_rs % EPVF) == 0 &&
                       (p.b_bs % EPVF) == 0 && (p.g_rs % EPVF) == 0 && (p.g_bs % EPVF) == 0 &&
                       aligned16(p.B) && aligned16(p.G);
+  if (vec_ok && algo != TSGU_ALGO_ROWSPLIT && p.K / EPVF <= 128 && m < 0xffffffffLL &&
+      p.b_rs * (int64_t)sizeof(V) < 0xffffffffLL && aligned16(p.rowptr) && aligned16(p.colind)) {
+    const int64_t kv = p.K / EPVF;
+    if (kv <= 4) return launch_sddmm_tile<V, I, 4, 1>(p, nnz_total, s);
+    if (kv <= 8) return launch_sddmm_tile<V, I, 8, 1>(p, nnz_total, s);
+    if (kv <= 16) return launch_sddmm_tile<V, I, 16, 1>(p, nnz_total, s);
+    if (kv <= 32) return launch_sddmm_tile<V, I, 32, 1>(p, nnz_total, s);
+    if (kv <= 64) return launch_sddmm_tile<V, I, 32, 2>(p, nnz_total, s);
+    return launch_sddmm_tile<V, I, 32, 4>(p, nnz_total, s);
+  }
   if (vec_ok) {
     const int64_t kv = p.K / EPVF;
     if (kv <= 4) return launch_sddmm<V, I, EPVF, 4, 1>(p, s);
@@ -234,7 +408,6 @@ extern "C" int tsgu_sddmm_csr(const void* rowptr, const void* colind, const void
                               int64_t rowptr_bstride, int64_t nnz_bstride, int64_t nnz_total, int64_t g_bs,
                               int64_t g_rs, int64_t g_cs, int64_t b_bs, int64_t b_rs, int64_t b_cs,
                               int val_dtype, int idx_dtype, int algo, void* stream) {
-  (void)m;
   if (batch < 0 || n < 0 || K < 0) return TSGU_ERR_SHAPE;
   if (algo != TSGU_ALGO_AUTO && algo != TSGU_ALGO_ROWSPLIT && algo != TSGU_ALGO_MERGE) return TSGU_ERR_ALGO;
   if (batch == 0 || n == 0 || nnz_total == 0) return 0;
@@ -245,7 +418,7 @@ extern "C" int tsgu_sddmm_csr(const void* rowptr, const void* colind, const void
     p.batch = batch; p.n = n; p.K = K;
     p.rowptr_bstride = rowptr_bstride; p.nnz_bstride = nnz_bstride;
     p.g_bs = g_bs; p.g_rs = g_rs; p.g_cs = g_cs; p.b_bs = b_bs; p.b_rs = b_rs; p.b_cs = b_cs;
-    return tsgu::sddmm_dispatch<V, I>(p, tsgu::as_stream(stream));
+    return tsgu::sddmm_dispatch<V, I>(p, m, nnz_total, algo, tsgu::as_stream(stream));
   }));
   return 0;
 }

@@ -9,7 +9,10 @@
 // request, then broadcasts them with shuffles and keeps U independent B-row loads in flight
 // before the FMA chain (HBM/L2-latency hiding by ILP; no tensor cores: 2 flop per 4-16 B).
 // Accumulation is in CSR order inside a row (deterministic, no atomics).
+#include <type_traits>
+
 #include "common.cuh"
+#include "tile.cuh"
 
 namespace tsgu {
 
@@ -115,11 +118,200 @@ static int launch_rowsplit(const SpmmParams<V, I>& p, cudaStream_t s) {
   return launch_status();
 }
 
+
+// =============================================================================================
+// Fast path: persistent row-tile kernel, sparse operand staged by the bulk-copy engine (tile.cuh).
+// Requirements (checked by the dispatcher): 128-bit addressable dense operands, no value
+// permutation, K <= 32*4 vectors, m < 2^32.
+// =============================================================================================
+template <typename V, typename I, int LPR, int VPL, int U, bool EXACT, bool PERM>
+__global__ void __launch_bounds__(256, 3) spmm_tile_kernel(const SpmmParams<V, I> p, const int64_t tiles_per_item,
+                                                        const int64_t num_tiles, const int64_t rowptr_len,
+                                                        const int64_t nnz_len) {
+  using Acc = typename VT<V>::Acc;
+  using Cfg = TileCfg<V, I, PERM ? 2 : 1>;
+  using Smem = typename Cfg::Smem;
+  constexpr int EPV = 16 / sizeof(V);
+  constexpr int R = Cfg::TILE_ROWS, CAP = Cfg::CAP, AI = Cfg::ALN_I, AV = Cfg::ALN_V;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int gl = lane % LPR;
+  const unsigned gmask = group_mask<LPR>(lane);
+  const int group = tid / LPR;
+  constexpr int GROUPS = 256 / LPR;
+  const int kv = (int)(p.K / EPV);                      // vectors per dense row
+  const uint32_t row_bytes = (uint32_t)(p.b_rs * sizeof(V));  // dense row pitch in bytes (< 4 GiB)
+  // lane validity per vector slot (all true when EXACT: K fills LPR*VPL vectors)
+  bool on[VPL];
+#pragma unroll
+  for (int w = 0; w < VPL; ++w) on[w] = EXACT || (w * LPR + gl < kv);
+
+  if (tid == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) mbar_init(&sm.full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  TileProducer<V, I, PERM ? 2 : 1> prod{p.rowptr, p.colind, p.vals, p.perm, p.n, p.rowptr_bstride, p.nnz_bstride,
+                                tiles_per_item, rowptr_len, nnz_len};
+  int64_t nxt_s = 0, nxt_e = 0;
+  const int64_t t0 = blockIdx.x;
+  if (tid == 0 && t0 < num_tiles) {
+    int64_t s0, e0;
+    prod.bounds(t0, s0, e0);
+    prod.issue(sm.st[0], &sm.full[0], t0, s0, e0);
+    if (t0 + gridDim.x < num_tiles) prod.bounds(t0 + gridDim.x, nxt_s, nxt_e);
+  }
+
+  int it = 0;
+  for (int64_t t = t0; t < num_tiles; t += gridDim.x, ++it) {
+    const int stage = it & 1;
+    if (tid == 0) {
+      const int64_t tn = t + gridDim.x;
+      if (tn < num_tiles) {
+        prod.issue(sm.st[stage ^ 1], &sm.full[stage ^ 1], tn, nxt_s, nxt_e);
+        if (tn + gridDim.x < num_tiles) prod.bounds(tn + gridDim.x, nxt_s, nxt_e);
+      }
+    }
+    mbar_wait(&sm.full[stage], (uint32_t)((it >> 1) & 1));
+
+    const TileCoord c = tile_coord<R>(t, tiles_per_item, p.n);
+    const auto& st = sm.st[stage];
+    const int rp_shift = (int)((c.item * p.rowptr_bstride + c.r0) & (AI - 1));
+    const int64_t nnz_off = c.item * p.nnz_bstride;
+    const int64_t s_abs = (int64_t)st.rp[rp_shift] + nnz_off;
+    const int64_t e_abs = (int64_t)st.rp[rp_shift + c.rows] + nnz_off;
+    const bool staged = (e_abs - s_abs) <= CAP && e_abs > s_abs;
+    const I* scol = st.col + (int)(s_abs & (AI - 1));
+    const V* sval = st.val + (int)(s_abs & (AV - 1));
+    const I* sprm = st.prm + (int)(s_abs & (AI - 1));
+    // this lane's 16-byte column slice of the item's dense operand
+    const char* Bb = reinterpret_cast<const char*>(p.B + c.item * p.b_bs) + (size_t)gl * 16;
+
+    for (int lr = group; lr < c.rows; lr += GROUPS) {
+      const int64_t e0 = (int64_t)st.rp[rp_shift + lr] + nnz_off;
+      const int64_t e1 = (int64_t)st.rp[rp_shift + lr + 1] + nnz_off;
+      Acc acc[VPL][EPV];
+#pragma unroll
+      for (int w = 0; w < VPL; ++w)
+#pragma unroll
+        for (int i = 0; i < EPV; ++i) acc[w][i] = Acc(0);
+
+      for (int64_t base = e0; base < e1; base += LPR) {
+        const int64_t e = base + gl;
+        uint32_t cu = 0;
+        Acc v = Acc(0);
+        if (e < e1) {
+          if (staged) {
+            cu = (uint32_t)scol[(int)(e - s_abs)];
+            if constexpr (PERM) v = load_scalar<V>(p.vals + (int64_t)sprm[(int)(e - s_abs)]);
+            else v = VT<V>::to_acc(sval[(int)(e - s_abs)]);
+          } else {
+            cu = (uint32_t)__ldg(p.colind + e);
+            v = load_scalar<V>(p.vals + (PERM ? (int64_t)__ldg(p.perm + e) : e));
+          }
+        }
+        const int cnt = (int)min((int64_t)LPR, e1 - base);
+        int j = 0;
+        for (; j + U <= cnt; j += U) {  // full groups: U*VPL independent 128-bit loads, then the FMAs
+          uint4 b[U][VPL];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const uint32_t cj = shfl_idx(gmask, cu, j + u, LPR);
+            const char* brow = Bb + (uint64_t)cj * row_bytes;
+#pragma unroll
+            for (int w = 0; w < VPL; ++w) {
+              if (EXACT || on[w]) b[u][w] = __ldg(reinterpret_cast<const uint4*>(brow + w * (LPR * 16)));
+              else b[u][w] = make_uint4(0, 0, 0, 0);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const Acc vj = shfl_idx(gmask, v, j + u, LPR);
+#pragma unroll
+            for (int w = 0; w < VPL; ++w) {
+              Acc x[EPV];
+              Raw<V, EPV> raw;
+              raw.bits = b[u][w];
+              raw_unpack<V, EPV>(raw, x);
+#pragma unroll
+              for (int i = 0; i < EPV; ++i) acc[w][i] = fma(vj, x[i], acc[w][i]);
+            }
+          }
+        }
+        for (; j < cnt; ++j) {  // ragged tail, one entry at a time
+          const uint32_t cj = shfl_idx(gmask, cu, j, LPR);
+          const Acc vj = shfl_idx(gmask, v, j, LPR);
+          const char* brow = Bb + (uint64_t)cj * row_bytes;
+#pragma unroll
+          for (int w = 0; w < VPL; ++w) {
+            if (EXACT || on[w]) {
+              Acc x[EPV];
+              Raw<V, EPV> raw;
+              raw.bits = __ldg(reinterpret_cast<const uint4*>(brow + w * (LPR * 16)));
+              raw_unpack<V, EPV>(raw, x);
+#pragma unroll
+              for (int i = 0; i < EPV; ++i) acc[w][i] = fma(vj, x[i], acc[w][i]);
+            }
+          }
+        }
+      }
+      V* Crow = p.C + c.item * p.c_bs + (c.r0 + lr) * p.ldc;
+#pragma unroll
+      for (int w = 0; w < VPL; ++w)
+        if (EXACT || on[w]) store_vec<V, EPV>(Crow + (int64_t)(w * LPR + gl) * EPV, acc[w]);
+    }
+    __syncthreads();  // everyone is done with this stage before it is refilled
+  }
+}
+
+template <typename V, typename I, int LPR, int VPL, bool PERM>
+static int launch_tile(const SpmmParams<V, I>& p, int64_t nnz_total, cudaStream_t s) {
+  using Cfg = TileCfg<V, I, PERM ? 2 : 1>;
+  constexpr int U = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
+  constexpr int EPV = 16 / sizeof(V);
+  const bool exact = (p.K / EPV) == (int64_t)LPR * VPL;
+  auto kern = exact ? spmm_tile_kernel<V, I, LPR, VPL, U, true, PERM> : spmm_tile_kernel<V, I, LPR, VPL, U, false, PERM>;
+  const int smem = (int)sizeof(typename Cfg::Smem);
+  static_assert(sizeof(typename Cfg::Smem) <= 48 * 1024, "stay under the default dynamic smem limit");
+  static int ctas_per_sm[2] = {0, 0};  // per instantiation; same answer on every B200 of the box
+  if (ctas_per_sm[exact] == 0) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem) != cudaSuccess || occ < 1) occ = 1;
+    ctas_per_sm[exact] = occ;
+  }
+  const int64_t tiles_per_item = (p.n + Cfg::TILE_ROWS - 1) / Cfg::TILE_ROWS;
+  const int64_t num_tiles = tiles_per_item * p.batch;
+  int64_t grid = (int64_t)kNumSMs * ctas_per_sm[exact];
+  if (grid > num_tiles) grid = num_tiles;
+  const int64_t rowptr_len = p.nnz_bstride > 0 ? p.batch * p.rowptr_bstride : p.batch * p.n + 1;
+  kern<<<(unsigned)grid, 256, smem, s>>>(p, tiles_per_item, num_tiles, rowptr_len, nnz_total);
+  count_launch();
+  return launch_status();
+}
+
 template <typename V, typename I>
-static int spmm_dispatch(const SpmmParams<V, I>& p, cudaStream_t s) {
+static int spmm_dispatch(const SpmmParams<V, I>& p, int64_t m, int64_t nnz_total, int algo, cudaStream_t s) {
   constexpr int EPVF = 16 / sizeof(V);
   const bool vec_ok = p.b_cs == 1 && (p.K % EPVF) == 0 && (p.b_rs % EPVF) == 0 && (p.b_bs % EPVF) == 0 &&
                       (p.ldc % EPVF) == 0 && (p.c_bs % EPVF) == 0 && aligned16(p.B) && aligned16(p.C);
+  if (vec_ok && algo != TSGU_ALGO_ROWSPLIT && p.K / EPVF <= 128 && m < 0xffffffffLL &&
+      p.b_rs * (int64_t)sizeof(V) < 0xffffffffLL && aligned16(p.rowptr) && aligned16(p.colind) &&
+      aligned16(p.vals) && aligned16(p.perm)) {
+    const int64_t kv = p.K / EPVF;
+#define TSGU_TILE(LPR_, VPL_) \
+  return p.perm ? launch_tile<V, I, LPR_, VPL_, true>(p, nnz_total, s) : launch_tile<V, I, LPR_, VPL_, false>(p, nnz_total, s)
+    if (kv <= 4) TSGU_TILE(4, 1);
+    if (kv <= 8) TSGU_TILE(8, 1);
+    if (kv <= 16) TSGU_TILE(16, 1);
+    if (kv <= 32) TSGU_TILE(32, 1);
+    if (kv <= 64) TSGU_TILE(32, 2);
+    TSGU_TILE(32, 4);
+#undef TSGU_TILE
+  }
   if (vec_ok) {
     const int64_t kv = p.K / EPVF;  // vectors per row
     if (kv <= 4) return launch_rowsplit<V, I, EPVF, 4, 1>(p, s);
@@ -142,7 +334,7 @@ extern "C" int tsgu_spmm_csr(const void* rowptr, const void* colind, const void*
                              int64_t b_bs, int64_t b_rs, int64_t b_cs, int64_t c_bs, int64_t ldc,
                              int val_dtype, int idx_dtype, int algo, void* workspace,
                              size_t workspace_bytes, void* stream) {
-  (void)m; (void)nnz_total; (void)workspace; (void)workspace_bytes;
+  (void)workspace; (void)workspace_bytes;
   if (batch < 0 || n < 0 || K < 0) return TSGU_ERR_SHAPE;
   if (algo != TSGU_ALGO_AUTO && algo != TSGU_ALGO_ROWSPLIT && algo != TSGU_ALGO_MERGE) return TSGU_ERR_ALGO;
   if (batch == 0 || n == 0 || K == 0) return 0;
@@ -153,7 +345,7 @@ extern "C" int tsgu_spmm_csr(const void* rowptr, const void* colind, const void*
     p.batch = batch; p.n = n; p.K = K;
     p.rowptr_bstride = rowptr_bstride; p.nnz_bstride = nnz_bstride;
     p.b_bs = b_bs; p.b_rs = b_rs; p.b_cs = b_cs; p.c_bs = c_bs; p.ldc = ldc;
-    return tsgu::spmm_dispatch<V, I>(p, tsgu::as_stream(stream));
+    return tsgu::spmm_dispatch<V, I>(p, m, nnz_total, algo, tsgu::as_stream(stream));
   }));
   return 0;
 }
