@@ -39,7 +39,7 @@ CONFIGS = {
               desc="COO 4096x4096 @1% x dense 4096x64 fp32 (BASELINE configs[0])"),
     "2": dict(kind="csr_uniform", n=65536, m=65536, per_row=16, K=128, dtype="f32", batch=8,
               desc="batched CSR b=8 65536x65536 16 nnz/row x dense 65536x128 fp32 int32 (BASELINE configs[1])"),
-    "3": dict(kind="stencil", D=128, K=32, dtype="f32", batch=None,
+    "3": dict(kind="stencil", D=128, K=32, dtype="f32", batch=None, b_colmajor=True,
               desc="27-point 128^3 stencil CSR (55.7M nnz) x dense 2097152x32 fp32 (BASELINE configs[2])"),
     "4": dict(kind="rmat", scale=22, K=128, dtype="bf16", batch=None,
               desc="R-MAT 2^22 rows ~64M nnz x dense 2^22x128 bf16 (BASELINE configs[3])"),
@@ -67,6 +67,8 @@ def build_inputs(cfg, device, batch_slice=None, seed_shift=0):
     else:
         raise ValueError(cfg["kind"])
     B, G = W.dense_operands(tuple(A.shape), cfg["K"], dt, device, seed=100 + seed_shift)
+    if cfg.get("b_colmajor"):  # rsample hands sparse_mm eps.t(): a column-major view
+        B = B.t().contiguous().t()
     if batch_slice is not None and A.dim() == 3:
         lo, hi = batch_slice
         A = torch.sparse_csr_tensor(A.crow_indices()[lo:hi].contiguous(), A.col_indices()[lo:hi].contiguous(),

@@ -74,7 +74,9 @@ TSGU_API int64_t tsgu_launch_count(void);
  * `perm` (nullable, idx_dtype): value of stored entry e is vals[perm[e]] instead of vals[e].
  * C is written row-major: C[t, r, k] = C + t*c_bs + r*ldc + k; every row is written (empty
  * rows get zeros), so C needs no initialisation.
- * Workspace: tsgu_spmm_workspace_bytes() (0 for ROWSPLIT).
+ * algo: AUTO / ROWSPLIT pick the row-split kernels (persistent bulk-copy-staged tiles when the
+ * operands are 128-bit addressable); MERGE (batch = 1 only, else ignored) the nnz-balanced merge-path
+ * kernel for skewed row lengths.  Workspace: tsgu_spmm_workspace_bytes() (0 unless algo = MERGE).
  * ---------------------------------------------------------------------------------- */
 TSGU_API int tsgu_spmm_csr(const void* rowptr, const void* colind, const void* vals, const void* perm,
                   const void* B, void* C,
@@ -93,6 +95,7 @@ TSGU_API size_t tsgu_spmm_workspace_bytes(int64_t batch, int64_t n, int64_t K, i
  *   repeat_interleave(arange(n), diff(crow)) of sparse_matmul.py:190-192 (never materialised).
  * `out_index` (nullable, idx_dtype): dst(e) = out_index[e], entries with out_index[e] < 0 are
  * skipped (used to write COO gradients back in A's storage order); null: dst(e) = e.
+ * Workspace: tsgu_sddmm_workspace_bytes() (0 unless algo = MERGE).
  * ---------------------------------------------------------------------------------- */
 TSGU_API int tsgu_sddmm_csr(const void* rowptr, const void* colind, const void* out_index,
                    const void* G, const void* B, void* out,
@@ -100,7 +103,9 @@ TSGU_API int tsgu_sddmm_csr(const void* rowptr, const void* colind, const void* 
                    int64_t rowptr_bstride, int64_t nnz_bstride, int64_t nnz_total,
                    int64_t g_bs, int64_t g_rs, int64_t g_cs,
                    int64_t b_bs, int64_t b_rs, int64_t b_cs,
-                   int val_dtype, int idx_dtype, int algo, void* stream);
+                   int val_dtype, int idx_dtype, int algo,
+                   void* workspace, size_t workspace_bytes, void* stream);
+TSGU_API size_t tsgu_sddmm_workspace_bytes(int64_t batch, int64_t n, int64_t nnz_total, int algo);
 
 /* Order-agnostic COO variant: row/col are int64 arrays of length nnz (torch COO indices,
  * sparse_matmul.py:184-185); out[e] = <G[row[e],:], B[col[e],:]>.  Also the kernel the

@@ -345,3 +345,72 @@ def test_memory_no_nnz_by_k_temporaries():
     extra = torch.cuda.max_memory_allocated() - base
     one_temp = n * per_row * K * 4
     assert extra < 0.25 * one_temp, (extra, one_temp)
+
+
+# ---------------------------------------------------------------- merge-path (nnz-balanced) kernels
+def _skewed_csr(n, m, seed, dtype=torch.float32, index_dtype=torch.int32, hub_rows=(0, 7, 300), hub_len=9000):
+    """Power-law-ish rows: a few hubs far longer than a tile, many empty rows, short rows in between."""
+    g = torch.Generator().manual_seed(seed)
+    cnt = torch.randint(0, 4, (n,), generator=g)
+    cnt[torch.rand(n, generator=g) < 0.4] = 0
+    for r in hub_rows:
+        if r < n:
+            cnt[r] = min(hub_len, m)
+    cnt[n - 1] = min(2500, m)  # long last row: the path ends inside a cut row
+    crow = torch.zeros(n + 1, dtype=torch.int64)
+    crow[1:] = cnt.cumsum(0)
+    col = torch.cat([torch.randperm(m, generator=g)[:c].sort().values for c in cnt.tolist()])
+    vals = torch.rand(col.numel(), generator=g, dtype=torch.float64).to(dtype)
+    return torch.sparse_csr_tensor(crow.to(index_dtype).to(DEV), col.to(index_dtype).to(DEV), vals.to(DEV), (n, m))
+
+
+@pytest.mark.parametrize("K", [16, 32, 64, 128, 160, 512])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.bfloat16])
+def test_merge_path_vs_oracle(K, dtype, monkeypatch):
+    """Forced merge-path SpMM / SDDMM / transposed SpMM on skewed rows vs the oracle."""
+    import torchsparsegradutils_b200 as tsgu
+
+    monkeypatch.setenv("TSGU_B200_ALGO", "merge")
+    tsgu.clear_pattern_cache()
+    n, m = 1500, 12000
+    A = _skewed_csr(n, m, seed=K, dtype=dtype)
+    _check(A, torch.rand(m, K, device=DEV, dtype=dtype), torch.rand(n, K, device=DEV, dtype=dtype))
+    tsgu.clear_pattern_cache()
+
+
+@pytest.mark.parametrize("index_dtype", [torch.int32, torch.int64])
+def test_merge_path_auto_selected_and_matches_rowsplit(index_dtype, monkeypatch):
+    """The skew heuristic picks merge-path by itself, and both kernel families agree bit for bit on
+    the integer side (pattern) and to fp32 rounding on values."""
+    import torchsparsegradutils_b200 as tsgu
+    from torchsparsegradutils_b200 import _native as nat
+    from torchsparsegradutils_b200._pattern import csr_pattern
+
+    tsgu.clear_pattern_cache()
+    A = _skewed_csr(4000, 20000, seed=1, index_dtype=index_dtype, hub_len=15000)
+    assert csr_pattern(A).algo == nat.ALGO_MERGE
+    B = torch.rand(20000, 64, device=DEV)
+    G = torch.rand(4000, 64, device=DEV)
+    C1, gA1, gB1 = _run(A, B, G)
+    monkeypatch.setenv("TSGU_B200_ALGO", "rowsplit")
+    tsgu.clear_pattern_cache()
+    C2, gA2, gB2 = _run(A, B, G)
+    tsgu.clear_pattern_cache()
+    torch.testing.assert_close(C1, C2, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(gA1.values(), gA2.values(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(gB1, gB2, rtol=1e-5, atol=1e-6)
+
+
+def test_merge_path_coo_unsorted(monkeypatch):
+    """COO input (value permutation staged instead of values) through the merge-path kernels."""
+    import torchsparsegradutils_b200 as tsgu
+
+    monkeypatch.setenv("TSGU_B200_ALGO", "merge")
+    tsgu.clear_pattern_cache()
+    Acsr = _skewed_csr(700, 5000, seed=3, index_dtype=torch.int64, hub_len=4000)
+    crow, col, vals = Acsr.crow_indices(), Acsr.col_indices(), Acsr.values()
+    rows = torch.repeat_interleave(torch.arange(700, device=DEV), crow[1:] - crow[:-1])
+    sh = torch.randperm(col.numel(), device=DEV)
+    A = torch.sparse_coo_tensor(torch.stack([rows, col])[:, sh], vals[sh], (700, 5000))
+    _check(A, torch.rand(5000, 32, device=DEV), torch.rand(700, 32, device=DEV))
+    tsgu.clear_pattern_cache()

@@ -14,7 +14,7 @@ from ctypes import c_char_p, c_int, c_int64, c_size_t, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtsgu_b200.so")
+LIB_PATH = os.environ.get("TSGU_B200_LIB") or os.path.join(_HERE, "libtsgu_b200.so")  # env override: kernel-variant experiments only
 
 # enums of include/tsgu_b200.h
 F32, F64, BF16 = 0, 1, 2
@@ -32,7 +32,8 @@ _SIGNATURES = {
     "tsgu_launch_count": (_L, []),
     "tsgu_spmm_csr": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _I, _I, _P, _Z, _P]),
     "tsgu_spmm_workspace_bytes": (_Z, [_L, _L, _L, _L, _I, _I]),
-    "tsgu_sddmm_csr": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _I, _I, _P]),
+    "tsgu_sddmm_csr": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _I, _I, _P, _Z, _P]),
+    "tsgu_sddmm_workspace_bytes": (_Z, [_L, _L, _L, _I]),
     "tsgu_sddmm_coo": (_I, [_P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _I, _P]),
     "tsgu_coo_sort": (_I, [_P, _I, _L, _L, _P, _I, _P, _P, _I, _P, _Z, _P]),
     "tsgu_coo_sort_workspace_bytes": (_Z, [_I, _L, _I]),

@@ -103,9 +103,10 @@ def _strides(x: torch.Tensor):
     return (bs if x.shape[0] > 1 else 0, rs if x.shape[1] > 1 else 0, cs if x.shape[2] > 1 else 1)
 
 
-def spmm(pat: CsrPattern, vals: torch.Tensor, dense: torch.Tensor, algo: int = nat.ALGO_AUTO,
+def spmm(pat: CsrPattern, vals: torch.Tensor, dense: torch.Tensor, algo: Optional[int] = None,
          tag: str = "spmm") -> torch.Tensor:
     """out[t] = A[t] @ dense[t]; dense is (batch, m, K) (any strides); returns contiguous (batch, n, K)."""
+    algo = pat.algo if algo is None else algo
     dense = prepare_dense(_as3d(dense))
     K = dense.shape[-1]
     out = torch.empty((pat.batch, pat.n, K), dtype=dense.dtype, device=dense.device)
@@ -127,20 +128,25 @@ def spmm(pat: CsrPattern, vals: torch.Tensor, dense: torch.Tensor, algo: int = n
 
 
 def sddmm(pat: CsrPattern, G: torch.Tensor, B: torch.Tensor, out_index: Optional[torch.Tensor], nnz_out: int,
-          algo: int = nat.ALGO_AUTO) -> torch.Tensor:
+          algo: Optional[int] = None) -> torch.Tensor:
     """values[dst(e)] = <G[t, r_e], B[t, c_e]> for every stored entry of the pattern."""
+    algo = pat.algo if algo is None else algo
     G = prepare_dense(_as3d(G))
     B = prepare_dense(_as3d(B))
     out = torch.empty(nnz_out, dtype=B.dtype, device=B.device)
     if nnz_out == 0:
         return out
     dev = B.device
+    L = nat.lib()
     with torch.cuda.device(dev), _timed("sddmm", dev):
-        nat.check(nat.lib().tsgu_sddmm_csr(nat.ptr(pat.rowptr), nat.ptr(pat.colind), nat.ptr(out_index),
+        ws_bytes = L.tsgu_sddmm_workspace_bytes(pat.batch, pat.n, pat.nnz_total, algo)
+        ws = nat.workspace(ws_bytes, dev) if ws_bytes else None
+        nat.check(L.tsgu_sddmm_csr(nat.ptr(pat.rowptr), nat.ptr(pat.colind), nat.ptr(out_index),
                                            G.data_ptr(), B.data_ptr(), out.data_ptr(), pat.batch, pat.n, pat.m,
                                            B.shape[-1], pat.rowptr_bstride, pat.nnz_bstride, pat.nnz_total,
                                            *_strides(G), *_strides(B),
-                                           nat.val_enum(B.dtype), pat.idx, algo, nat.stream_ptr(dev)),
+                                           nat.val_enum(B.dtype), pat.idx, algo, nat.ptr(ws),
+                                           ws.numel() if ws is not None else 0, nat.stream_ptr(dev)),
                   "tsgu_sddmm_csr")
     return out
 

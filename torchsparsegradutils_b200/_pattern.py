@@ -14,6 +14,7 @@ recycled for a different pattern while the entry lives, and it is invalidated by
 from __future__ import annotations
 
 import ctypes
+import os
 import threading
 from collections import OrderedDict
 from dataclasses import dataclass, field
@@ -56,6 +57,7 @@ class CsrPattern:
     nnz_bstride: int
     nnz_total: int
     idx: int  # nat.I32 / nat.I64
+    algo: int = nat.ALGO_AUTO  # kernel family chosen once per pattern from its row-length skew
     keep: tuple = ()  # tensors whose storage must outlive this pattern (cache-key owners)
     _transpose: Optional["CsrPattern"] = field(default=None, repr=False)
     _lock: threading.Lock = field(default_factory=threading.Lock, repr=False)
@@ -71,6 +73,27 @@ class CsrPattern:
                 if self._transpose is None:
                     self._transpose = _build_transpose(self)
         return self._transpose
+
+
+_ALGO_ENV = {"auto": None, "rowsplit": nat.ALGO_ROWSPLIT, "merge": nat.ALGO_MERGE}
+
+
+def choose_algo(rowptr: torch.Tensor, batch: int, n: int, nnz_total: int) -> int:
+    """Row-split (regular rows) or merge-path (skewed rows) -- decided once per pattern.
+
+    Merge-path pays a fix-up pass and per-entry row bookkeeping, so it is only picked when one row
+    is both long in absolute terms and far above the mean (power-law graphs).  One host sync per new
+    pattern.  ``TSGU_B200_ALGO=auto|rowsplit|merge`` overrides the heuristic (benchmarking only).
+    """
+    forced = _ALGO_ENV.get(os.environ.get("TSGU_B200_ALGO", "auto").lower())
+    if forced is not None:
+        return forced
+    if batch != 1 or nnz_total == 0 or n == 0:
+        return nat.ALGO_AUTO
+    flat = rowptr.reshape(-1)  # batch == 1: torch batched CSR keeps a leading dim of 1
+    max_row = int((flat[1:] - flat[:-1]).max())
+    mean = nnz_total / n
+    return nat.ALGO_MERGE if (max_row > 1024 and max_row > 32 * mean) else nat.ALGO_AUTO
 
 
 def _internal_idx(batch: int, rows: int, cols: int, nnz: int) -> int:
@@ -96,7 +119,8 @@ def _build_transpose(p: CsrPattern) -> CsrPattern:
     if p.perm is not None and p.nnz_total > 0:
         # entries of p are themselves a permutation of the caller's value storage: compose once
         permT = p.perm.to(odt).index_select(0, permT.long()) if p.perm.dtype != odt else p.perm.index_select(0, permT.long())
-    return CsrPattern(rowptrT, colindT, permT, p.batch, p.m, p.n, p.m, 0, p.nnz_total, out_idx, keep=(p,))
+    return CsrPattern(rowptrT, colindT, permT, p.batch, p.m, p.n, p.m, 0, p.nnz_total, out_idx,
+                      algo=choose_algo(rowptrT, p.batch, p.m, p.nnz_total), keep=(p,))
 
 
 def _cache_get(key):
@@ -131,7 +155,7 @@ def csr_pattern(A: torch.Tensor) -> CsrPattern:
     crow_c, col_c = crow.contiguous(), col.contiguous()
     nnz_item = col_c.shape[-1]
     pat = CsrPattern(crow_c, col_c, None, batch, n, m, n + 1, nnz_item, batch * nnz_item,
-                     nat.idx_enum(crow.dtype), keep=(crow, col))
+                     nat.idx_enum(crow.dtype), algo=choose_algo(crow_c, batch, n, batch * nnz_item), keep=(crow, col))
     _cache_put(key, pat)
     return pat
 
@@ -180,7 +204,7 @@ def _coo_to_flat_csr(indices: torch.Tensor, batch: int, n: int, m: int, perm: Op
         nat.check(nat.lib().tsgu_coo_to_csr(nat.ptr(indices), ndim, nnz, indices.stride(0), batch, n, nat.ptr(perm),
                                             nat.ptr(rowptr), nat.ptr(colind), idx, nat.stream_ptr(dev)),
                   "tsgu_coo_to_csr")
-    return CsrPattern(rowptr, colind, perm, batch, n, m, n, 0, nnz, idx, keep=keep)
+    return CsrPattern(rowptr, colind, perm, batch, n, m, n, 0, nnz, idx, algo=choose_algo(rowptr, batch, n, nnz), keep=keep)
 
 
 def coo_pattern(A: torch.Tensor) -> CooPattern:

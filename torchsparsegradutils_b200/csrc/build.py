@@ -21,7 +21,7 @@ FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr", "-Xptxas", "-v",
     "-DTSGU_BUILD",
-]
+] + os.environ.get("TSGU_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _stale(target: str, deps: list[str]) -> bool:

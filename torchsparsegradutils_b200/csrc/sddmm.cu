@@ -7,6 +7,7 @@
 // group of LPR lanes holds are reduced with a halving butterfly: (NB-1) + log2(LPR/NB) shuffles per
 // NB entries instead of NB*log2(LPR).
 #include "common.cuh"
+#include "merge.cuh"
 #include "tile.cuh"
 
 namespace tsgu {
@@ -145,7 +146,7 @@ static int launch_sddmm(const SddmmParams<V, I>& p, cudaStream_t s) {
 // Fast path: persistent row-tile kernel; rowptr / colind staged by the bulk-copy engine (tile.cuh).
 // =============================================================================================
 template <typename V, typename I, int LPR, int VPL, int NB, int U, bool EXACT>
-__global__ void __launch_bounds__(256, 3) sddmm_tile_kernel(const SddmmParams<V, I> p, const int64_t tiles_per_item,
+__global__ void __launch_bounds__(256, TSGU_TILE_MINB) sddmm_tile_kernel(const SddmmParams<V, I> p, const int64_t tiles_per_item,
                                                             const int64_t num_tiles, const int64_t rowptr_len,
                                                             const int64_t nnz_len) {
   using Acc = typename VT<V>::Acc;
@@ -280,7 +281,7 @@ template <typename V, typename I, int LPR, int VPL>
 static int launch_sddmm_tile(const SddmmParams<V, I>& p, int64_t nnz_total, cudaStream_t s) {
   using Cfg = TileCfg<V, I, 0>;
   constexpr int NB = LPR < 16 ? LPR : 16;
-  constexpr int U0 = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
+  constexpr int U0 = TSGU_TILE_LOADS / VPL;
   constexpr int U = U0 < NB ? U0 : NB;
   constexpr int EPV = 16 / sizeof(V);
   const bool exact = (p.K / EPV) == (int64_t)LPR * VPL;
@@ -304,13 +305,19 @@ static int launch_sddmm_tile(const SddmmParams<V, I>& p, int64_t nnz_total, cuda
 }
 
 template <typename V, typename I>
-static int sddmm_dispatch(const SddmmParams<V, I>& p, int64_t m, int64_t nnz_total, int algo, cudaStream_t s) {
+static int sddmm_dispatch(const SddmmParams<V, I>& p, int64_t m, int64_t nnz_total, int algo, void* ws, size_t ws_bytes,
+                          cudaStream_t s) {
   constexpr int EPVF = 16 / sizeof(V);
   const bool vec_ok = p.b_cs == 1 && p.g_cs == 1 && (p.K % EPVF) == 0 && (p.b_rs % EPVF) == 0 &&
                       (p.b_bs % EPVF) == 0 && (p.g_rs % EPVF) == 0 && (p.g_bs % EPVF) == 0 &&
                       aligned16(p.B) && aligned16(p.G);
-  if (vec_ok && algo != TSGU_ALGO_ROWSPLIT && p.K / EPVF <= 128 && m < 0xffffffffLL &&
-      p.b_rs * (int64_t)sizeof(V) < 0xffffffffLL && aligned16(p.rowptr) && aligned16(p.colind)) {
+  const bool fast_ok = vec_ok && p.K / EPVF <= 128 && m < 0xffffffffLL && p.b_rs * (int64_t)sizeof(V) < 0xffffffffLL &&
+                       aligned16(p.rowptr) && aligned16(p.colind);
+  if (fast_ok && algo == TSGU_ALGO_MERGE && p.batch == 1)
+    return sddmm_merge_dispatch<V, I>(p.rowptr, p.colind, p.out_index, p.G, p.B, p.out, p.n, p.K, nnz_total, p.g_rs, p.b_rs,
+                                      ws, ws_bytes, s);
+  const bool tiny = (p.batch * ((p.n + 63) / 64)) < 2 * kNumSMs;
+  if (fast_ok && algo != TSGU_ALGO_ROWSPLIT && !tiny) {
     const int64_t kv = p.K / EPVF;
     if (kv <= 4) return launch_sddmm_tile<V, I, 4, 1>(p, nnz_total, s);
     if (kv <= 8) return launch_sddmm_tile<V, I, 8, 1>(p, nnz_total, s);
@@ -407,7 +414,8 @@ extern "C" int tsgu_sddmm_csr(const void* rowptr, const void* colind, const void
                               const void* B, void* out, int64_t batch, int64_t n, int64_t m, int64_t K,
                               int64_t rowptr_bstride, int64_t nnz_bstride, int64_t nnz_total, int64_t g_bs,
                               int64_t g_rs, int64_t g_cs, int64_t b_bs, int64_t b_rs, int64_t b_cs,
-                              int val_dtype, int idx_dtype, int algo, void* stream) {
+                              int val_dtype, int idx_dtype, int algo, void* workspace, size_t workspace_bytes,
+                              void* stream) {
   if (batch < 0 || n < 0 || K < 0) return TSGU_ERR_SHAPE;
   if (algo != TSGU_ALGO_AUTO && algo != TSGU_ALGO_ROWSPLIT && algo != TSGU_ALGO_MERGE) return TSGU_ERR_ALGO;
   if (batch == 0 || n == 0 || nnz_total == 0) return 0;
@@ -418,8 +426,13 @@ extern "C" int tsgu_sddmm_csr(const void* rowptr, const void* colind, const void
     p.batch = batch; p.n = n; p.K = K;
     p.rowptr_bstride = rowptr_bstride; p.nnz_bstride = nnz_bstride;
     p.g_bs = g_bs; p.g_rs = g_rs; p.g_cs = g_cs; p.b_bs = b_bs; p.b_rs = b_rs; p.b_cs = b_cs;
-    return tsgu::sddmm_dispatch<V, I>(p, m, nnz_total, algo, tsgu::as_stream(stream));
+    return tsgu::sddmm_dispatch<V, I>(p, m, nnz_total, algo, workspace, workspace_bytes, tsgu::as_stream(stream));
   }));
+  return 0;
+}
+
+extern "C" size_t tsgu_sddmm_workspace_bytes(int64_t batch, int64_t n, int64_t nnz_total, int algo) {
+  if (algo == TSGU_ALGO_MERGE && batch == 1) return tsgu::sddmm_merge_workspace_bytes(n, nnz_total);
   return 0;
 }
 

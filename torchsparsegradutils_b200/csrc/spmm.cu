@@ -12,6 +12,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "merge.cuh"
 #include "tile.cuh"
 
 namespace tsgu {
@@ -125,7 +126,7 @@ static int launch_rowsplit(const SpmmParams<V, I>& p, cudaStream_t s) {
 // permutation, K <= 32*4 vectors, m < 2^32.
 // =============================================================================================
 template <typename V, typename I, int LPR, int VPL, int U, bool EXACT, bool PERM>
-__global__ void __launch_bounds__(256, 3) spmm_tile_kernel(const SpmmParams<V, I> p, const int64_t tiles_per_item,
+__global__ void __launch_bounds__(256, TSGU_TILE_MINB) spmm_tile_kernel(const SpmmParams<V, I> p, const int64_t tiles_per_item,
                                                         const int64_t num_tiles, const int64_t rowptr_len,
                                                         const int64_t nnz_len) {
   using Acc = typename VT<V>::Acc;
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(256, 3) spmm_tile_kernel(const SpmmParams<V, I
 template <typename V, typename I, int LPR, int VPL, bool PERM>
 static int launch_tile(const SpmmParams<V, I>& p, int64_t nnz_total, cudaStream_t s) {
   using Cfg = TileCfg<V, I, PERM ? 2 : 1>;
-  constexpr int U = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
+  constexpr int U = TSGU_TILE_LOADS / VPL;  // independent 128-bit loads in flight per lane
   constexpr int EPV = 16 / sizeof(V);
   const bool exact = (p.K / EPV) == (int64_t)LPR * VPL;
   auto kern = exact ? spmm_tile_kernel<V, I, LPR, VPL, U, true, PERM> : spmm_tile_kernel<V, I, LPR, VPL, U, false, PERM>;
@@ -294,13 +295,19 @@ static int launch_tile(const SpmmParams<V, I>& p, int64_t nnz_total, cudaStream_
 }
 
 template <typename V, typename I>
-static int spmm_dispatch(const SpmmParams<V, I>& p, int64_t m, int64_t nnz_total, int algo, cudaStream_t s) {
+static int spmm_dispatch(const SpmmParams<V, I>& p, int64_t m, int64_t nnz_total, int algo, void* ws, size_t ws_bytes,
+                         cudaStream_t s) {
   constexpr int EPVF = 16 / sizeof(V);
   const bool vec_ok = p.b_cs == 1 && (p.K % EPVF) == 0 && (p.b_rs % EPVF) == 0 && (p.b_bs % EPVF) == 0 &&
                       (p.ldc % EPVF) == 0 && (p.c_bs % EPVF) == 0 && aligned16(p.B) && aligned16(p.C);
-  if (vec_ok && algo != TSGU_ALGO_ROWSPLIT && p.K / EPVF <= 128 && m < 0xffffffffLL &&
-      p.b_rs * (int64_t)sizeof(V) < 0xffffffffLL && aligned16(p.rowptr) && aligned16(p.colind) &&
-      aligned16(p.vals) && aligned16(p.perm)) {
+  const bool fast_ok = vec_ok && p.K / EPVF <= 128 && m < 0xffffffffLL && p.b_rs * (int64_t)sizeof(V) < 0xffffffffLL &&
+                       aligned16(p.rowptr) && aligned16(p.colind) && aligned16(p.vals) && aligned16(p.perm);
+  if (fast_ok && algo == TSGU_ALGO_MERGE && p.batch == 1 && p.ldc == p.K)
+    return spmm_merge_dispatch<V, I>(p.rowptr, p.colind, p.vals, p.perm, p.B, p.C, p.n, p.K, nnz_total, p.b_rs, p.ldc, ws,
+                                     ws_bytes, s);
+  // small problems cannot fill 148 SMs with 64-row tiles: one row per lane group, one CTA per 256/LPR rows
+  const bool tiny = (p.batch * ((p.n + 63) / 64)) < 2 * kNumSMs;
+  if (fast_ok && algo != TSGU_ALGO_ROWSPLIT && !tiny) {
     const int64_t kv = p.K / EPVF;
 #define TSGU_TILE(LPR_, VPL_) \
   return p.perm ? launch_tile<V, I, LPR_, VPL_, true>(p, nnz_total, s) : launch_tile<V, I, LPR_, VPL_, false>(p, nnz_total, s)
@@ -334,7 +341,6 @@ extern "C" int tsgu_spmm_csr(const void* rowptr, const void* colind, const void*
                              int64_t b_bs, int64_t b_rs, int64_t b_cs, int64_t c_bs, int64_t ldc,
                              int val_dtype, int idx_dtype, int algo, void* workspace,
                              size_t workspace_bytes, void* stream) {
-  (void)workspace; (void)workspace_bytes;
   if (batch < 0 || n < 0 || K < 0) return TSGU_ERR_SHAPE;
   if (algo != TSGU_ALGO_AUTO && algo != TSGU_ALGO_ROWSPLIT && algo != TSGU_ALGO_MERGE) return TSGU_ERR_ALGO;
   if (batch == 0 || n == 0 || K == 0) return 0;
@@ -345,13 +351,13 @@ extern "C" int tsgu_spmm_csr(const void* rowptr, const void* colind, const void*
     p.batch = batch; p.n = n; p.K = K;
     p.rowptr_bstride = rowptr_bstride; p.nnz_bstride = nnz_bstride;
     p.b_bs = b_bs; p.b_rs = b_rs; p.b_cs = b_cs; p.c_bs = c_bs; p.ldc = ldc;
-    return tsgu::spmm_dispatch<V, I>(p, m, nnz_total, algo, tsgu::as_stream(stream));
+    return tsgu::spmm_dispatch<V, I>(p, m, nnz_total, algo, workspace, workspace_bytes, tsgu::as_stream(stream));
   }));
   return 0;
 }
 
 extern "C" size_t tsgu_spmm_workspace_bytes(int64_t batch, int64_t n, int64_t K, int64_t nnz_total,
                                             int val_dtype, int algo) {
-  (void)batch; (void)n; (void)K; (void)nnz_total; (void)val_dtype; (void)algo;
+  if (algo == TSGU_ALGO_MERGE && batch == 1) return tsgu::spmm_merge_workspace_bytes(n, K, nnz_total, val_dtype);
   return 0;
 }

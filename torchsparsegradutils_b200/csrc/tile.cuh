@@ -9,6 +9,17 @@
 #pragma once
 #include "common.cuh"
 
+// tunables (overridable at build time for experiments: TSGU_EXTRA_NVCC_FLAGS="-DTSGU_TILE_MINB=2 ...")
+#ifndef TSGU_TILE_MINB
+#define TSGU_TILE_MINB 3    // resident CTAs per SM the register allocation aims for
+#endif
+#ifndef TSGU_TILE_LOADS
+#define TSGU_TILE_LOADS 8   // 128-bit dense-row loads in flight per lane before the FMA chain
+#endif
+#ifndef TSGU_TILE_ROWS
+#define TSGU_TILE_ROWS 64
+#endif
+
 namespace tsgu {
 
 // ------------------------------------------------------------------ mbarrier / bulk copy PTX
@@ -44,7 +55,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // (SpMM over a transposed / COO-derived structure: the value of entry e is vals[perm[e]]).
 template <typename V, typename I, int VALS>
 struct TileCfg {
-  static constexpr int TILE_ROWS = 64;
+  static constexpr int TILE_ROWS = TSGU_TILE_ROWS;
   // entries of colind / vals staged per tile: 16 KB per stage (2048 for fp32 + int32)
   static constexpr int CAP = (16384 / (int)(sizeof(I) + (VALS == 1 ? sizeof(V) : VALS == 2 ? sizeof(I) : 0))) & ~15;
   static constexpr int ALN_I = 16 / (int)sizeof(I);
