@@ -232,6 +232,15 @@ def main():
     else:
         shard = None
     A, B, G = build_inputs(cfg, dev, shard)
+    row_sharded = world > 1 and not cfg.get("batch") and A.layout == torch.sparse_csr
+    if row_sharded:
+        # one large matrix: nnz-balanced row blocks, B replicated, grad_B all-reduced over NVLink
+        from torchsparsegradutils_b200 import distributed as D
+
+        bounds = D.nnz_balanced_row_blocks(A.crow_indices(), world)
+        A = D.shard_rows_csr(A, bounds[rank], bounds[rank + 1])
+        G = G[bounds[rank]:bounds[rank + 1]].contiguous()
+        config_out["sharding"] = f"nnz-balanced row blocks over {world} ranks, B replicated, grad_B all-reduce (NCCL)"
     st = problem_stats(A, cfg["K"])
     A.requires_grad_(True)
     B.requires_grad_(True)
@@ -239,7 +248,7 @@ def main():
     def step():
         A.grad = None
         B.grad = None
-        C = sparse_mm(A, B)
+        C = D.sparse_mm_row_sharded(A, B) if row_sharded else sparse_mm(A, B)
         C.backward(G)
         return C
 
@@ -289,12 +298,17 @@ def main():
         gbs = alg / (rec["ms"] * 1e-3) / 1e9
         kernels[tag] = {"ms": rec["ms"], "launches": rec["launches"], "alg_bytes": alg, "achieved_gbs": gbs,
                         "frac": gbs / peak, "gather_gbs": st["gather_bytes_per_pass"] / (rec["ms"] * 1e-3) / 1e9}
+    # measured DRAM traffic per launch from the committed ncu --set full capture of this workload
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", f"r1_cfg{args.config}_traffic.json")
+    if os.path.exists(tpath) and world == 1:
+        traffic = {k: v["dram_bytes"] for k, v in json.load(open(tpath))["kernels"].items()}
     dom = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
     roofline = None
     if dom:
         d = kernels[dom]
         roofline = {"bound": "hbm", "kernel": dom, "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": d["frac"], "traffic": None, "peak_source": peak_src,
+                    "frac": d["frac"], "traffic": traffic.get(dom), "alg_bytes": d["alg_bytes"], "peak_source": peak_src,
                     "share_of_step": d["ms"] / ms_step, "l2_gather_gbs": d["gather_gbs"]}
     step_gbs = st["alg"]["total"] / (ms_step * 1e-3) / 1e9
 
@@ -311,7 +325,7 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if cfg.get("batch") else "weak",
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic", "config": config_out,
                 "clocks": clk.report(), "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline,
                 "cpu_baseline": cpu_base, "gflops": st["flops"] * (nnz_all / st["nnz"]) / (ms_step * 1e-3) / 1e9,
