@@ -315,7 +315,8 @@ def main():
     # ---- e2e: same step through the public API from pinned host buffers
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(A.detach(), B.detach(), G, args.e2e_steps, dev, dist, sparse_mm)
+        e2e = run_e2e(A.detach(), B.detach(), G, args.e2e_steps, dev, dist,
+                      (lambda a, b: D.sparse_mm_row_sharded(a, b)) if row_sharded else sparse_mm)
         e2e["value"] = (nnz_all / (e2e.pop("ms_per_step_max") * 1e-3))
 
     cpu_base = None

@@ -170,10 +170,12 @@ TSGU_API int tsgu_gather_values(const void* in, const void* perm, void* out, int
 TSGU_API int tsgu_segment_sum_values(const void* in, const void* perm, const void* seg, void* out,
                             int64_t nseg, int val_dtype, int idx_dtype, void* stream);
 
-/* Strided dense -> row-major contiguous (B.reshape(-1,K) copy of sparse_matmul.py:153 when B is a
- * permuted view, e.g. from _batch_sparse_mv, distributions/sparse_multivariate_normal.py:96,100). */
+/* Strided dense -> strided dense layout change, coalesced on both sides.  Used for the
+ * B.reshape(-1,K) copy of sparse_matmul.py:153 when B is a transposed / permuted view (e.g. from
+ * _batch_sparse_mv, distributions/sparse_multivariate_normal.py:96,100) and to hand grad_B back in
+ * B's own memory layout (what autograd would otherwise re-stride with a generic copy). */
 TSGU_API int tsgu_pack_dense(const void* src, void* dst, int64_t batch, int64_t rows, int64_t cols,
-                    int64_t s_bs, int64_t s_rs, int64_t s_cs, int64_t d_bs, int64_t d_ld,
+                    int64_t s_bs, int64_t s_rs, int64_t s_cs, int64_t d_bs, int64_t d_rs, int64_t d_cs,
                     int val_dtype, void* stream);
 
 #ifdef __cplusplus

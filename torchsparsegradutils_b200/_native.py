@@ -45,7 +45,7 @@ _SIGNATURES = {
     "tsgu_csr_transpose_workspace_bytes": (_Z, [_L, _L, _L, _I]),
     "tsgu_gather_values": (_I, [_P, _P, _P, _L, _I, _I, _P]),
     "tsgu_segment_sum_values": (_I, [_P, _P, _P, _P, _L, _I, _I, _P]),
-    "tsgu_pack_dense": (_I, [_P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _I, _P]),
+    "tsgu_pack_dense": (_I, [_P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -249,28 +249,45 @@ __global__ void segment_sum_kernel(const V* __restrict__ in, const I* __restrict
   }
 }
 
-// strided -> row-major through a 32x33 shared tile so both sides are coalesced for transposed views
+// strided -> strided dense copy (layout change).  A block owns PACK_R consecutive rows and walks the
+// columns in chunks of 32 through a padded shared tile; the read phase runs threadIdx along whichever
+// source dimension is contiguous, the write phase along whichever destination dimension is, so
+// row-major <-> column-major (transposed-view) conversions are coalesced on both sides with
+// PACK_R/8 independent loads per thread in flight.
+constexpr int PACK_R = 128;
 template <typename V>
-__global__ void pack_dense_kernel(const V* __restrict__ src, V* __restrict__ dst, int64_t rows, int64_t cols,
-                                  int64_t s_bs, int64_t s_rs, int64_t s_cs, int64_t d_bs, int64_t d_ld,
-                                  int64_t tiles_r, int64_t tiles_c) {
-  __shared__ V tile[32][33];
-  const int64_t t = blockIdx.x;
-  const int64_t item = t / (tiles_r * tiles_c);
-  const int64_t rem = t - item * tiles_r * tiles_c;
-  const int64_t r0 = (rem / tiles_c) * 32, c0 = (rem % tiles_c) * 32;
+__global__ void __launch_bounds__(256) pack_dense_kernel(const V* __restrict__ src, V* __restrict__ dst, int64_t rows,
+                                                         int64_t cols, int64_t s_bs, int64_t s_rs, int64_t s_cs,
+                                                         int64_t d_bs, int64_t d_rs, int64_t d_cs,
+                                                         int64_t blocks_per_item) {
+  __shared__ V tile[PACK_R][33];
+  const int64_t item = blockIdx.x / blocks_per_item;
+  const int64_t r0 = (blockIdx.x - item * blocks_per_item) * PACK_R;
   const V* sp = src + item * s_bs;
   V* dp = dst + item * d_bs;
-  const bool col_fast = (s_cs <= s_rs);  // which source index should vary fastest across threadIdx.x
-  for (int y = threadIdx.y; y < 32; y += blockDim.y) {
-    const int64_t r = col_fast ? r0 + y : r0 + threadIdx.x;
-    const int64_t c = col_fast ? c0 + threadIdx.x : c0 + y;
-    if (r < rows && c < cols) tile[r - r0][c - c0] = sp[r * s_rs + c * s_cs];
-  }
-  __syncthreads();
-  for (int y = threadIdx.y; y < 32; y += blockDim.y) {
-    const int64_t r = r0 + y, c = c0 + threadIdx.x;
-    if (r < rows && c < cols) dp[r * d_ld + c] = tile[y][threadIdx.x];
+  const bool src_row_fast = s_rs < s_cs;  // contiguous along rows (column-major view)
+  const bool dst_row_fast = d_rs < d_cs;
+  for (int64_t c0 = 0; c0 < cols; c0 += 32) {
+    if (src_row_fast) {
+      const int r = threadIdx.x % PACK_R;
+      for (int c = threadIdx.x / PACK_R; c < 32; c += 256 / PACK_R)
+        if (r0 + r < rows && c0 + c < cols) tile[r][c] = sp[(r0 + r) * s_rs + (c0 + c) * s_cs];
+    } else {
+      const int c = threadIdx.x % 32;
+      for (int r = threadIdx.x / 32; r < PACK_R; r += 8)
+        if (r0 + r < rows && c0 + c < cols) tile[r][c] = sp[(r0 + r) * s_rs + (c0 + c) * s_cs];
+    }
+    __syncthreads();
+    if (dst_row_fast) {
+      const int r = threadIdx.x % PACK_R;
+      for (int c = threadIdx.x / PACK_R; c < 32; c += 256 / PACK_R)
+        if (r0 + r < rows && c0 + c < cols) dp[(r0 + r) * d_rs + (c0 + c) * d_cs] = tile[r][c];
+    } else {
+      const int c = threadIdx.x % 32;
+      for (int r = threadIdx.x / 32; r < PACK_R; r += 8)
+        if (r0 + r < rows && c0 + c < cols) dp[(r0 + r) * d_rs + (c0 + c) * d_cs] = tile[r][c];
+    }
+    __syncthreads();
   }
 }
 
@@ -438,15 +455,16 @@ extern "C" int tsgu_segment_sum_values(const void* in, const void* perm, const v
 }
 
 extern "C" int tsgu_pack_dense(const void* src, void* dst, int64_t batch, int64_t rows, int64_t cols, int64_t s_bs,
-                               int64_t s_rs, int64_t s_cs, int64_t d_bs, int64_t d_ld, int val_dtype, void* stream) {
+                               int64_t s_rs, int64_t s_cs, int64_t d_bs, int64_t d_rs, int64_t d_cs, int val_dtype,
+                               void* stream) {
   if (batch < 0 || rows < 0 || cols < 0) return TSGU_ERR_SHAPE;
   if (batch == 0 || rows == 0 || cols == 0) return 0;
   cudaStream_t s = as_stream(stream);
-  const int64_t tr = (rows + 31) / 32, tc = (cols + 31) / 32;
-  const int64_t blocks = batch * tr * tc;
+  const int64_t bpi = (rows + PACK_R - 1) / PACK_R;
+  const int64_t blocks = batch * bpi;
   if (blocks > 0x7fffffffLL) return TSGU_ERR_RANGE;
   TSGU_DISPATCH_VAL(val_dtype, {
-    pack_dense_kernel<V><<<(unsigned)blocks, dim3(32, 8), 0, s>>>((const V*)src, (V*)dst, rows, cols, s_bs, s_rs, s_cs, d_bs, d_ld, tr, tc);
+    pack_dense_kernel<V><<<(unsigned)blocks, 256, 0, s>>>((const V*)src, (V*)dst, rows, cols, s_bs, s_rs, s_cs, d_bs, d_rs, d_cs, bpi);
     count_launch();
   });
   return launch_status();

@@ -373,7 +373,8 @@ static int launch_spmm_merge(const I* rowptr, const I* colind, const V* vals, co
                              cudaStream_t s) {
   using Acc = typename VT<V>::Acc;
   constexpr int EPV = 16 / sizeof(V);
-  constexpr int U = TSGU_TILE_LOADS / VPL;
+  constexpr int U0 = TSGU_TILE_LOADS / VPL;
+  constexpr int U = U0 < LPR ? U0 : LPR;
   const int64_t num_tiles = (rows + nnz + MERGE_P - 1) / MERGE_P;
   const int64_t kpad = (int64_t)LPR * VPL * EPV;
   const size_t part_bytes = ((size_t)(num_tiles + 1) * 2 * sizeof(int64_t) + 255) / 256 * 256;

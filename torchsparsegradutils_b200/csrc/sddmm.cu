@@ -148,12 +148,12 @@ static int launch_sddmm(const SddmmParams<V, I>& p, cudaStream_t s) {
 template <typename V, typename I, int LPR, int VPL, int NB, int U, bool EXACT>
 __global__ void __launch_bounds__(256, TSGU_TILE_MINB) sddmm_tile_kernel(const SddmmParams<V, I> p, const int64_t tiles_per_item,
                                                             const int64_t num_tiles, const int64_t rowptr_len,
-                                                            const int64_t nnz_len) {
+                                                            const int64_t nnz_len, const int tile_rows) {
   using Acc = typename VT<V>::Acc;
   using Cfg = TileCfg<V, I, 0>;
   using Smem = typename Cfg::Smem;
   constexpr int EPV = 16 / sizeof(V);
-  constexpr int R = Cfg::TILE_ROWS, CAP = Cfg::CAP, AI = Cfg::ALN_I;
+  constexpr int CAP = Cfg::CAP, AI = Cfg::ALN_I;
   constexpr int LPE = LPR / NB;
   static_assert(NB % U == 0, "batch is processed in chunks of U entries");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256, TSGU_TILE_MINB) sddmm_tile_kernel(const S
   __syncthreads();
 
   TileProducer<V, I, 0> prod{p.rowptr, p.colind, nullptr, nullptr, p.n, p.rowptr_bstride, p.nnz_bstride,
-                             tiles_per_item, rowptr_len, nnz_len};
+                             tiles_per_item, rowptr_len, nnz_len, tile_rows};
   int64_t nxt_s = 0, nxt_e = 0;
   const int64_t t0 = blockIdx.x;
   if (tid == 0 && t0 < num_tiles) {
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256, TSGU_TILE_MINB) sddmm_tile_kernel(const S
     }
     mbar_wait(&sm.full[stage], (uint32_t)((it >> 1) & 1));
 
-    const TileCoord c = tile_coord<R>(t, tiles_per_item, p.n);
+    const TileCoord c = tile_coord(t, tiles_per_item, p.n, tile_rows);
     const auto& st = sm.st[stage];
     const int rp_shift = (int)((c.item * p.rowptr_bstride + c.r0) & (AI - 1));
     const int64_t nnz_off = c.item * p.nnz_bstride;
@@ -287,19 +287,20 @@ static int launch_sddmm_tile(const SddmmParams<V, I>& p, int64_t nnz_total, cuda
   const bool exact = (p.K / EPV) == (int64_t)LPR * VPL;
   auto kern = exact ? sddmm_tile_kernel<V, I, LPR, VPL, NB, U, true> : sddmm_tile_kernel<V, I, LPR, VPL, NB, U, false>;
   const int smem = (int)sizeof(typename Cfg::Smem);
-  static_assert(sizeof(typename Cfg::Smem) <= 48 * 1024, "stay under the default dynamic smem limit");
   static int ctas_per_sm[2] = {0, 0};
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return (int)cudaGetLastError();
   if (ctas_per_sm[exact] == 0) {
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem) != cudaSuccess || occ < 1) occ = 1;
     ctas_per_sm[exact] = occ;
   }
-  const int64_t tiles_per_item = (p.n + Cfg::TILE_ROWS - 1) / Cfg::TILE_ROWS;
+  const int tile_rows = pick_tile_rows(p.batch * p.n, nnz_total, Cfg::CAP, 256 / LPR);
+  const int64_t tiles_per_item = (p.n + tile_rows - 1) / tile_rows;
   const int64_t num_tiles = tiles_per_item * p.batch;
   int64_t grid = (int64_t)kNumSMs * ctas_per_sm[exact];
   if (grid > num_tiles) grid = num_tiles;
   const int64_t rowptr_len = p.nnz_bstride > 0 ? p.batch * p.rowptr_bstride : p.batch * p.n + 1;
-  kern<<<(unsigned)grid, 256, smem, s>>>(p, tiles_per_item, num_tiles, rowptr_len, nnz_total);
+  kern<<<(unsigned)grid, 256, smem, s>>>(p, tiles_per_item, num_tiles, rowptr_len, nnz_total, tile_rows);
   count_launch();
   return launch_status();
 }
@@ -316,14 +317,24 @@ static int sddmm_dispatch(const SddmmParams<V, I>& p, int64_t m, int64_t nnz_tot
   if (fast_ok && algo == TSGU_ALGO_MERGE && p.batch == 1)
     return sddmm_merge_dispatch<V, I>(p.rowptr, p.colind, p.out_index, p.G, p.B, p.out, p.n, p.K, nnz_total, p.g_rs, p.b_rs,
                                       ws, ws_bytes, s);
-  const bool tiny = (p.batch * ((p.n + 63) / 64)) < 2 * kNumSMs;
+  const bool tiny = p.batch * p.n < 64 * 2 * kNumSMs;  // fewer rows than ~64 per resident CTA
   if (fast_ok && algo != TSGU_ALGO_ROWSPLIT && !tiny) {
     const int64_t kv = p.K / EPVF;
     if (kv <= 4) return launch_sddmm_tile<V, I, 4, 1>(p, nnz_total, s);
     if (kv <= 8) return launch_sddmm_tile<V, I, 8, 1>(p, nnz_total, s);
+#if TSGU_LPR_CAP == 8
+    if (kv <= 16) return launch_sddmm_tile<V, I, 8, 2>(p, nnz_total, s);
+    if (kv <= 32) return launch_sddmm_tile<V, I, 8, 4>(p, nnz_total, s);
+    if (kv <= 64) return launch_sddmm_tile<V, I, 16, 4>(p, nnz_total, s);
+#elif TSGU_LPR_CAP == 16
+    if (kv <= 16) return launch_sddmm_tile<V, I, 16, 1>(p, nnz_total, s);
+    if (kv <= 32) return launch_sddmm_tile<V, I, 16, 2>(p, nnz_total, s);
+    if (kv <= 64) return launch_sddmm_tile<V, I, 16, 4>(p, nnz_total, s);
+#else
     if (kv <= 16) return launch_sddmm_tile<V, I, 16, 1>(p, nnz_total, s);
     if (kv <= 32) return launch_sddmm_tile<V, I, 32, 1>(p, nnz_total, s);
     if (kv <= 64) return launch_sddmm_tile<V, I, 32, 2>(p, nnz_total, s);
+#endif
     return launch_sddmm_tile<V, I, 32, 4>(p, nnz_total, s);
   }
   if (vec_ok) {

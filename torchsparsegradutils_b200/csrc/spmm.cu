@@ -128,12 +128,12 @@ static int launch_rowsplit(const SpmmParams<V, I>& p, cudaStream_t s) {
 template <typename V, typename I, int LPR, int VPL, int U, bool EXACT, bool PERM>
 __global__ void __launch_bounds__(256, TSGU_TILE_MINB) spmm_tile_kernel(const SpmmParams<V, I> p, const int64_t tiles_per_item,
                                                         const int64_t num_tiles, const int64_t rowptr_len,
-                                                        const int64_t nnz_len) {
+                                                        const int64_t nnz_len, const int tile_rows) {
   using Acc = typename VT<V>::Acc;
   using Cfg = TileCfg<V, I, PERM ? 2 : 1>;
   using Smem = typename Cfg::Smem;
   constexpr int EPV = 16 / sizeof(V);
-  constexpr int R = Cfg::TILE_ROWS, CAP = Cfg::CAP, AI = Cfg::ALN_I, AV = Cfg::ALN_V;
+  constexpr int CAP = Cfg::CAP, AI = Cfg::ALN_I, AV = Cfg::ALN_V;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256, TSGU_TILE_MINB) spmm_tile_kernel(const Sp
   __syncthreads();
 
   TileProducer<V, I, PERM ? 2 : 1> prod{p.rowptr, p.colind, p.vals, p.perm, p.n, p.rowptr_bstride, p.nnz_bstride,
-                                tiles_per_item, rowptr_len, nnz_len};
+                                tiles_per_item, rowptr_len, nnz_len, tile_rows};
   int64_t nxt_s = 0, nxt_e = 0;
   const int64_t t0 = blockIdx.x;
   if (tid == 0 && t0 < num_tiles) {
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256, TSGU_TILE_MINB) spmm_tile_kernel(const Sp
     }
     mbar_wait(&sm.full[stage], (uint32_t)((it >> 1) & 1));
 
-    const TileCoord c = tile_coord<R>(t, tiles_per_item, p.n);
+    const TileCoord c = tile_coord(t, tiles_per_item, p.n, tile_rows);
     const auto& st = sm.st[stage];
     const int rp_shift = (int)((c.item * p.rowptr_bstride + c.r0) & (AI - 1));
     const int64_t nnz_off = c.item * p.nnz_bstride;
@@ -272,24 +272,26 @@ __global__ void __launch_bounds__(256, TSGU_TILE_MINB) spmm_tile_kernel(const Sp
 template <typename V, typename I, int LPR, int VPL, bool PERM>
 static int launch_tile(const SpmmParams<V, I>& p, int64_t nnz_total, cudaStream_t s) {
   using Cfg = TileCfg<V, I, PERM ? 2 : 1>;
-  constexpr int U = TSGU_TILE_LOADS / VPL;  // independent 128-bit loads in flight per lane
+  constexpr int U0 = TSGU_TILE_LOADS / VPL;  // independent 128-bit loads in flight per lane ...
+  constexpr int U = U0 < LPR ? U0 : LPR;      // ... but never more entries than one batch holds
   constexpr int EPV = 16 / sizeof(V);
   const bool exact = (p.K / EPV) == (int64_t)LPR * VPL;
   auto kern = exact ? spmm_tile_kernel<V, I, LPR, VPL, U, true, PERM> : spmm_tile_kernel<V, I, LPR, VPL, U, false, PERM>;
   const int smem = (int)sizeof(typename Cfg::Smem);
-  static_assert(sizeof(typename Cfg::Smem) <= 48 * 1024, "stay under the default dynamic smem limit");
   static int ctas_per_sm[2] = {0, 0};  // per instantiation; same answer on every B200 of the box
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return (int)cudaGetLastError();
   if (ctas_per_sm[exact] == 0) {
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem) != cudaSuccess || occ < 1) occ = 1;
     ctas_per_sm[exact] = occ;
   }
-  const int64_t tiles_per_item = (p.n + Cfg::TILE_ROWS - 1) / Cfg::TILE_ROWS;
+  const int tile_rows = pick_tile_rows(p.batch * p.n, nnz_total, Cfg::CAP, 256 / LPR);
+  const int64_t tiles_per_item = (p.n + tile_rows - 1) / tile_rows;
   const int64_t num_tiles = tiles_per_item * p.batch;
   int64_t grid = (int64_t)kNumSMs * ctas_per_sm[exact];
   if (grid > num_tiles) grid = num_tiles;
   const int64_t rowptr_len = p.nnz_bstride > 0 ? p.batch * p.rowptr_bstride : p.batch * p.n + 1;
-  kern<<<(unsigned)grid, 256, smem, s>>>(p, tiles_per_item, num_tiles, rowptr_len, nnz_total);
+  kern<<<(unsigned)grid, 256, smem, s>>>(p, tiles_per_item, num_tiles, rowptr_len, nnz_total, tile_rows);
   count_launch();
   return launch_status();
 }
@@ -306,16 +308,28 @@ static int spmm_dispatch(const SpmmParams<V, I>& p, int64_t m, int64_t nnz_total
     return spmm_merge_dispatch<V, I>(p.rowptr, p.colind, p.vals, p.perm, p.B, p.C, p.n, p.K, nnz_total, p.b_rs, p.ldc, ws,
                                      ws_bytes, s);
   // small problems cannot fill 148 SMs with 64-row tiles: one row per lane group, one CTA per 256/LPR rows
-  const bool tiny = (p.batch * ((p.n + 63) / 64)) < 2 * kNumSMs;
+  const bool tiny = p.batch * p.n < 64 * 2 * kNumSMs;  // fewer rows than ~64 per resident CTA
   if (fast_ok && algo != TSGU_ALGO_ROWSPLIT && !tiny) {
     const int64_t kv = p.K / EPVF;
 #define TSGU_TILE(LPR_, VPL_) \
   return p.perm ? launch_tile<V, I, LPR_, VPL_, true>(p, nnz_total, s) : launch_tile<V, I, LPR_, VPL_, false>(p, nnz_total, s)
+    // narrower lane groups with more vectors per lane serve several rows per warp instruction, which
+    // divides the shuffle (col / val broadcast) traffic on the LSU return path (TSGU_LPR_CAP, tile.cuh)
     if (kv <= 4) TSGU_TILE(4, 1);
     if (kv <= 8) TSGU_TILE(8, 1);
+#if TSGU_LPR_CAP == 8
+    if (kv <= 16) TSGU_TILE(8, 2);
+    if (kv <= 32) TSGU_TILE(8, 4);
+    if (kv <= 64) TSGU_TILE(16, 4);
+#elif TSGU_LPR_CAP == 16
+    if (kv <= 16) TSGU_TILE(16, 1);
+    if (kv <= 32) TSGU_TILE(16, 2);
+    if (kv <= 64) TSGU_TILE(16, 4);
+#else
     if (kv <= 16) TSGU_TILE(16, 1);
     if (kv <= 32) TSGU_TILE(32, 1);
     if (kv <= 64) TSGU_TILE(32, 2);
+#endif
     TSGU_TILE(32, 4);
 #undef TSGU_TILE
   }

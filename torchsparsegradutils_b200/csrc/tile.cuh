@@ -11,13 +11,16 @@
 
 // tunables (overridable at build time for experiments: TSGU_EXTRA_NVCC_FLAGS="-DTSGU_TILE_MINB=2 ...")
 #ifndef TSGU_TILE_MINB
-#define TSGU_TILE_MINB 3    // resident CTAs per SM the register allocation aims for
+#define TSGU_TILE_MINB 2    // resident CTAs per SM the register allocation aims for
 #endif
 #ifndef TSGU_TILE_LOADS
-#define TSGU_TILE_LOADS 8   // 128-bit dense-row loads in flight per lane before the FMA chain
+#define TSGU_TILE_LOADS 16  // 128-bit dense-row loads in flight per lane before the FMA chain
+#endif
+#ifndef TSGU_LPR_CAP
+#define TSGU_LPR_CAP 8     // widest lane group the tile kernels use (8 / 16 / 32)
 #endif
 #ifndef TSGU_TILE_ROWS
-#define TSGU_TILE_ROWS 64
+#define TSGU_TILE_ROWS 128  // most rows a tile may hold; the launcher picks tile_rows <= this from nnz/row
 #endif
 
 namespace tsgu {
@@ -56,8 +59,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 template <typename V, typename I, int VALS>
 struct TileCfg {
   static constexpr int TILE_ROWS = TSGU_TILE_ROWS;
-  // entries of colind / vals staged per tile: 16 KB per stage (2048 for fp32 + int32)
-  static constexpr int CAP = (16384 / (int)(sizeof(I) + (VALS == 1 ? sizeof(V) : VALS == 2 ? sizeof(I) : 0))) & ~15;
+  // entries of colind / vals staged per tile: 32 KB per stage (4096 for fp32 + int32)
+  static constexpr int CAP = (32768 / (int)(sizeof(I) + (VALS == 1 ? sizeof(V) : VALS == 2 ? sizeof(I) : 0))) & ~15;
   static constexpr int ALN_I = 16 / (int)sizeof(I);
   static constexpr int ALN_V = 16 / (int)sizeof(V);
   static constexpr int STAGES = 2;
@@ -73,13 +76,23 @@ struct TileCfg {
   };
 };
 
+// rows per tile for a launch: as many as fit the staging capacity with 25 % slack for uneven rows,
+// capped by TSGU_TILE_ROWS, and a multiple of the number of lane groups so every group gets whole rows
+inline int pick_tile_rows(int64_t total_rows, int64_t nnz_total, int cap_entries, int groups) {
+  const double avg = total_rows > 0 ? (double)nnz_total / (double)total_rows : 0.0;
+  int64_t r = avg > 0 ? (int64_t)((double)cap_entries / (1.25 * avg)) : TSGU_TILE_ROWS;
+  if (r > TSGU_TILE_ROWS) r = TSGU_TILE_ROWS;
+  r = r / groups * groups;
+  if (r < groups) r = groups < TSGU_TILE_ROWS ? groups : TSGU_TILE_ROWS;
+  return (int)r;
+}
+
 struct TileCoord {
   int64_t item, r0;
   int rows;  // rows in this tile (<= TILE_ROWS)
 };
 
-template <int TILE_ROWS>
-__device__ __forceinline__ TileCoord tile_coord(int64_t t, int64_t tiles_per_item, int64_t n) {
+__device__ __forceinline__ TileCoord tile_coord(int64_t t, int64_t tiles_per_item, int64_t n, int TILE_ROWS) {
   TileCoord c;
   if (tiles_per_item < 0x7fffffffLL && t < 0x7fffffffLL) {  // 32-bit division in the common case
     c.item = (uint32_t)t / (uint32_t)tiles_per_item;
@@ -103,9 +116,10 @@ struct TileProducer {
   const V* vals;
   const I* perm;
   int64_t n, rowptr_bstride, nnz_bstride, tiles_per_item, rowptr_len, nnz_len;
+  int tile_rows;
 
   __device__ __forceinline__ void bounds(int64_t t, int64_t& s_abs, int64_t& e_abs) const {
-    const TileCoord c = tile_coord<Cfg::TILE_ROWS>(t, tiles_per_item, n);
+    const TileCoord c = tile_coord(t, tiles_per_item, n, tile_rows);
     const I* rp = rowptr + c.item * rowptr_bstride + c.r0;
     s_abs = (int64_t)__ldg(rp) + c.item * nnz_bstride;
     e_abs = (int64_t)__ldg(rp + c.rows) + c.item * nnz_bstride;
@@ -130,7 +144,7 @@ struct TileProducer {
 
   __device__ __forceinline__ void issue(typename Cfg::Stage& st, uint64_t* bar, int64_t t, int64_t s_abs,
                                         int64_t e_abs) const {
-    const TileCoord c = tile_coord<Cfg::TILE_ROWS>(t, tiles_per_item, n);
+    const TileCoord c = tile_coord(t, tiles_per_item, n, tile_rows);
     const int64_t rp_lo = c.item * rowptr_bstride + c.r0;
     uint32_t tx = span<I>(st.rp, rowptr, rp_lo, rp_lo + c.rows + 1, rowptr_len, bar);
     if ((e_abs - s_abs) <= Cfg::CAP && e_abs > s_abs) {

@@ -92,6 +92,8 @@ class SparseMatMul(torch.autograd.Function):
         ctx.batched = B.dim() == 3
         ctx.A_shape = A.size()
         ctx.B_shape = B.size()
+        # remember a non-contiguous (but dense) layout of B so grad_B can be handed back in it
+        ctx.B_strides = B.stride() if (not B.is_contiguous() and _ops.is_dense_non_overlapping(B)) else None
         A, B = A.detach(), B.detach()
 
         coalesced_vals = None
@@ -105,11 +107,14 @@ class SparseMatMul(torch.autograd.Function):
                 coalesced_vals = _ops.segment_sum_values(vals, pat.sort_perm, pat.seg, pat.nnz_unique)
                 vals = coalesced_vals
 
-        x = _ops.spmm(csr, vals, B, tag="spmm_fwd")
+        # a strided view of B (eps.t(), permute(1,2,0) from _batch_sparse_mv) is packed once here and the
+        # packed copy is what backward's SDDMM re-reads -- the reference re-copies it as well (:153)
+        Bk = _ops.prepare_dense(B if ctx.batched else B.unsqueeze(0))
+        x = _ops.spmm(csr, vals, Bk, tag="spmm_fwd")
         x = x if ctx.batched else x[0]
 
         ctx.pattern = pat
-        ctx.save_for_backward(A, B, *(() if coalesced_vals is None else (coalesced_vals,)))
+        ctx.save_for_backward(A, Bk, *(() if coalesced_vals is None else (coalesced_vals,)))
         return x
 
     @staticmethod
@@ -147,5 +152,7 @@ class SparseMatMul(torch.autograd.Function):
                 vals = A._values().contiguous()
             gradB = _ops.spmm(csr.transpose(), vals, grad, tag="spmm_gradB")
             gradB = gradB if ctx.batched else gradB[0]
+            if ctx.B_strides is not None:
+                gradB = _ops.restride_like(gradB, ctx.B_shape, ctx.B_strides)
 
         return gradA, gradB
