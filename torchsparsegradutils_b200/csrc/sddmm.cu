@@ -25,11 +25,11 @@ struct SddmmParams {
   int64_t g_bs, g_rs, g_cs, b_bs, b_rs, b_cs;
 };
 
-// Reduce NB per-lane partials across the LPR lanes of a group.  On return lane gl holds in p[0] the
-// total of entry (gl / (LPR/NB)).
+// Reduce NB per-lane partials across the LPR lanes of a group with a halving butterfly.
+// NB <= LPR: lane gl ends with the total of entry gl / (LPR/NB) in p[0].
+// NB >  LPR: lane gl ends with the totals of entries gl*(NB/LPR) + i in p[i], i < NB/LPR.
 template <typename Acc, int LPR, int NB>
 __device__ __forceinline__ void butterfly_reduce(Acc (&p)[NB], unsigned gmask, int gl) {
-  static_assert(NB <= LPR, "NB entries need NB lanes to land on");
   int width = NB;
 #pragma unroll
   for (int s = LPR / 2; s >= 1; s >>= 1) {
@@ -154,7 +154,9 @@ __global__ void __launch_bounds__(256, TSGU_TILE_MINB) sddmm_tile_kernel(const S
   using Smem = typename Cfg::Smem;
   constexpr int EPV = 16 / sizeof(V);
   constexpr int CAP = Cfg::CAP, AI = Cfg::ALN_I;
-  constexpr int LPE = LPR / NB;
+  constexpr int LPE = NB <= LPR ? LPR / NB : 1;  // lanes holding the same entry after the butterfly
+  constexpr int RPL = NB <= LPR ? 1 : NB / LPR;  // results per lane after the butterfly
+  constexpr int QC = (NB + LPR - 1) / LPR;       // column indices each lane holds per batch
   static_assert(NB % U == 0, "batch is processed in chunks of U entries");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -224,9 +226,13 @@ __global__ void __launch_bounds__(256, TSGU_TILE_MINB) sddmm_tile_kernel(const S
       }
 
       for (int64_t base = e0; base < e1; base += NB) {
-        const int64_t e = base + gl;
-        uint32_t cu = 0;
-        if (gl < NB && e < e1) cu = staged ? (uint32_t)scol[(int)(e - s_abs)] : (uint32_t)__ldg(p.colind + e);
+        uint32_t cu[QC];
+#pragma unroll
+        for (int q = 0; q < QC; ++q) {
+          const int64_t e = base + q * LPR + gl;
+          cu[q] = 0;
+          if (q * LPR + gl < NB && e < e1) cu[q] = staged ? (uint32_t)scol[(int)(e - s_abs)] : (uint32_t)__ldg(p.colind + e);
+        }
         const int cnt = (int)min((int64_t)NB, e1 - base);
         Acc part[NB];
 #pragma unroll
@@ -234,19 +240,40 @@ __global__ void __launch_bounds__(256, TSGU_TILE_MINB) sddmm_tile_kernel(const S
 
 #pragma unroll
         for (int j0 = 0; j0 < NB; j0 += U) {
-          if (j0 < cnt) {  // group-uniform
-            const bool full = (j0 + U <= cnt);
+          if (j0 + U <= cnt) {  // full group (group-uniform branch): unpredicated gathers
             uint4 b[U][VPL];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-              const uint32_t cj = shfl_idx(gmask, cu, j0 + u, LPR);
+              const uint32_t cj = shfl_idx(gmask, cu[(j0 + u) / LPR], (j0 + u) % LPR, LPR);
               const char* brow = Bb + (uint64_t)cj * row_bytes;
 #pragma unroll
               for (int w = 0; w < VPL; ++w) {
-                if ((full || j0 + u < cnt) && (EXACT || on[w]))
-                  b[u][w] = __ldg(reinterpret_cast<const uint4*>(brow + w * (LPR * 16)));
-                else
-                  b[u][w] = make_uint4(0, 0, 0, 0);
+                if (EXACT || on[w]) b[u][w] = __ldg(reinterpret_cast<const uint4*>(brow + w * (LPR * 16)));
+                else b[u][w] = make_uint4(0, 0, 0, 0);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+              for (int w = 0; w < VPL; ++w) {
+                Acc x[EPV];
+                Raw<V, EPV> raw;
+                raw.bits = b[u][w];
+                raw_unpack<V, EPV>(raw, x);
+#pragma unroll
+                for (int i = 0; i < EPV; ++i) part[j0 + u] = fma(g[w][i], x[i], part[j0 + u]);
+              }
+            }
+          } else if (j0 < cnt) {  // ragged end of the row
+            uint4 b[U][VPL];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const uint32_t cj = shfl_idx(gmask, cu[(j0 + u) / LPR], (j0 + u) % LPR, LPR);
+              const char* brow = Bb + (uint64_t)cj * row_bytes;
+#pragma unroll
+              for (int w = 0; w < VPL; ++w) {
+                if (j0 + u < cnt && (EXACT || on[w])) b[u][w] = __ldg(reinterpret_cast<const uint4*>(brow + w * (LPR * 16)));
+                else b[u][w] = make_uint4(0, 0, 0, 0);
               }
             }
 #pragma unroll
@@ -264,12 +291,17 @@ __global__ void __launch_bounds__(256, TSGU_TILE_MINB) sddmm_tile_kernel(const S
           }
         }
         butterfly_reduce<Acc, LPR, NB>(part, gmask, gl);
-        const int slot = gl / LPE;
-        if ((gl % LPE) == 0 && slot < cnt) {
-          const int64_t eo = base + slot;
-          int64_t dst = eo;
-          if (p.out_index) dst = (int64_t)__ldg(p.out_index + eo);
-          if (dst >= 0) p.out[dst] = VT<V>::from_acc(part[0]);
+        if ((gl % LPE) == 0) {
+#pragma unroll
+          for (int i = 0; i < RPL; ++i) {
+            const int slot = (gl / LPE) * RPL + i;
+            if (slot < cnt) {
+              const int64_t eo = base + slot;
+              int64_t dst = eo;
+              if (p.out_index) dst = (int64_t)__ldg(p.out_index + eo);
+              if (dst >= 0) p.out[dst] = VT<V>::from_acc(part[i]);
+            }
+          }
         }
       }
     }
@@ -280,7 +312,7 @@ __global__ void __launch_bounds__(256, TSGU_TILE_MINB) sddmm_tile_kernel(const S
 template <typename V, typename I, int LPR, int VPL>
 static int launch_sddmm_tile(const SddmmParams<V, I>& p, int64_t nnz_total, cudaStream_t s) {
   using Cfg = TileCfg<V, I, 0>;
-  constexpr int NB = LPR < 16 ? LPR : 16;
+  constexpr int NB = 16;  // entries per batch (butterfly leaves NB/LPR results per lane when NB > LPR)
   constexpr int U0 = TSGU_TILE_LOADS / VPL;
   constexpr int U = U0 < NB ? U0 : NB;
   constexpr int EPV = 16 / sizeof(V);

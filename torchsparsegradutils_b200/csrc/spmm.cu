@@ -201,61 +201,80 @@ __global__ void __launch_bounds__(256, TSGU_TILE_MINB) spmm_tile_kernel(const Sp
 #pragma unroll
         for (int i = 0; i < EPV; ++i) acc[w][i] = Acc(0);
 
-      for (int64_t base = e0; base < e1; base += LPR) {
-        const int64_t e = base + gl;
-        uint32_t cu = 0;
-        Acc v = Acc(0);
-        if (e < e1) {
-          if (staged) {
-            cu = (uint32_t)scol[(int)(e - s_abs)];
-            if constexpr (PERM) v = load_scalar<V>(p.vals + (int64_t)sprm[(int)(e - s_abs)]);
-            else v = VT<V>::to_acc(sval[(int)(e - s_abs)]);
-          } else {
-            cu = (uint32_t)__ldg(p.colind + e);
-            v = load_scalar<V>(p.vals + (PERM ? (int64_t)__ldg(p.perm + e) : e));
-          }
-        }
-        const int cnt = (int)min((int64_t)LPR, e1 - base);
-        int j = 0;
-        for (; j + U <= cnt; j += U) {  // full groups: U*VPL independent 128-bit loads, then the FMAs
-          uint4 b[U][VPL];
+      // a batch is 32 entries: every lane holds Q = 32/LPR (col, val) pairs, broadcast by shuffle;
+      // U dense-row gathers (x VPL vectors) are issued back to back before their FMAs
+      constexpr int Q = 32 / LPR;
+      for (int64_t base = e0; base < e1; base += 32) {
+        uint32_t cu[Q];
+        Acc v[Q];
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const uint32_t cj = shfl_idx(gmask, cu, j + u, LPR);
-            const char* brow = Bb + (uint64_t)cj * row_bytes;
-#pragma unroll
-            for (int w = 0; w < VPL; ++w) {
-              if (EXACT || on[w]) b[u][w] = __ldg(reinterpret_cast<const uint4*>(brow + w * (LPR * 16)));
-              else b[u][w] = make_uint4(0, 0, 0, 0);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const Acc vj = shfl_idx(gmask, v, j + u, LPR);
-#pragma unroll
-            for (int w = 0; w < VPL; ++w) {
-              Acc x[EPV];
-              Raw<V, EPV> raw;
-              raw.bits = b[u][w];
-              raw_unpack<V, EPV>(raw, x);
-#pragma unroll
-              for (int i = 0; i < EPV; ++i) acc[w][i] = fma(vj, x[i], acc[w][i]);
+        for (int q = 0; q < Q; ++q) {
+          const int64_t e = base + q * LPR + gl;
+          cu[q] = 0;
+          v[q] = Acc(0);
+          if (e < e1) {
+            if (staged) {
+              cu[q] = (uint32_t)scol[(int)(e - s_abs)];
+              if constexpr (PERM) v[q] = load_scalar<V>(p.vals + (int64_t)sprm[(int)(e - s_abs)]);
+              else v[q] = VT<V>::to_acc(sval[(int)(e - s_abs)]);
+            } else {
+              cu[q] = (uint32_t)__ldg(p.colind + e);
+              v[q] = load_scalar<V>(p.vals + (PERM ? (int64_t)__ldg(p.perm + e) : e));
             }
           }
         }
-        for (; j < cnt; ++j) {  // ragged tail, one entry at a time
-          const uint32_t cj = shfl_idx(gmask, cu, j, LPR);
-          const Acc vj = shfl_idx(gmask, v, j, LPR);
-          const char* brow = Bb + (uint64_t)cj * row_bytes;
+        const int cnt = (int)min((int64_t)32, e1 - base);
 #pragma unroll
-          for (int w = 0; w < VPL; ++w) {
-            if (EXACT || on[w]) {
-              Acc x[EPV];
-              Raw<V, EPV> raw;
-              raw.bits = __ldg(reinterpret_cast<const uint4*>(brow + w * (LPR * 16)));
-              raw_unpack<V, EPV>(raw, x);
+        for (int j0 = 0; j0 < 32; j0 += U) {
+          if (j0 + U <= cnt) {  // full group (group-uniform branch): no predicates on the loads
+            uint4 b[U][VPL];
 #pragma unroll
-              for (int i = 0; i < EPV; ++i) acc[w][i] = fma(vj, x[i], acc[w][i]);
+            for (int u = 0; u < U; ++u) {
+              const uint32_t cj = shfl_idx(gmask, cu[(j0 + u) / LPR], (j0 + u) % LPR, LPR);
+              const char* brow = Bb + (uint64_t)cj * row_bytes;
+#pragma unroll
+              for (int w = 0; w < VPL; ++w) {
+                if (EXACT || on[w]) b[u][w] = __ldg(reinterpret_cast<const uint4*>(brow + w * (LPR * 16)));
+                else b[u][w] = make_uint4(0, 0, 0, 0);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const Acc vj = shfl_idx(gmask, v[(j0 + u) / LPR], (j0 + u) % LPR, LPR);
+#pragma unroll
+              for (int w = 0; w < VPL; ++w) {
+                Acc x[EPV];
+                Raw<V, EPV> raw;
+                raw.bits = b[u][w];
+                raw_unpack<V, EPV>(raw, x);
+#pragma unroll
+                for (int i = 0; i < EPV; ++i) acc[w][i] = fma(vj, x[i], acc[w][i]);
+              }
+            }
+          } else if (j0 < cnt) {  // ragged end of the row: same batch, loads predicated
+            uint4 b[U][VPL];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const uint32_t cj = shfl_idx(gmask, cu[(j0 + u) / LPR], (j0 + u) % LPR, LPR);
+              const char* brow = Bb + (uint64_t)cj * row_bytes;
+#pragma unroll
+              for (int w = 0; w < VPL; ++w) {
+                if (j0 + u < cnt && (EXACT || on[w])) b[u][w] = __ldg(reinterpret_cast<const uint4*>(brow + w * (LPR * 16)));
+                else b[u][w] = make_uint4(0, 0, 0, 0);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const Acc vj = shfl_idx(gmask, v[(j0 + u) / LPR], (j0 + u) % LPR, LPR);  // 0 past the row end
+#pragma unroll
+              for (int w = 0; w < VPL; ++w) {
+                Acc x[EPV];
+                Raw<V, EPV> raw;
+                raw.bits = b[u][w];
+                raw_unpack<V, EPV>(raw, x);
+#pragma unroll
+                for (int i = 0; i < EPV; ++i) acc[w][i] = fma(vj, x[i], acc[w][i]);
+              }
             }
           }
         }
@@ -273,7 +292,7 @@ template <typename V, typename I, int LPR, int VPL, bool PERM>
 static int launch_tile(const SpmmParams<V, I>& p, int64_t nnz_total, cudaStream_t s) {
   using Cfg = TileCfg<V, I, PERM ? 2 : 1>;
   constexpr int U0 = TSGU_TILE_LOADS / VPL;  // independent 128-bit loads in flight per lane ...
-  constexpr int U = U0 < LPR ? U0 : LPR;      // ... but never more entries than one batch holds
+  constexpr int U = U0 < 32 ? U0 : 32;        // ... (a batch is 32 entries)
   constexpr int EPV = 16 / sizeof(V);
   const bool exact = (p.K / EPV) == (int64_t)LPR * VPL;
   auto kern = exact ? spmm_tile_kernel<V, I, LPR, VPL, U, true, PERM> : spmm_tile_kernel<V, I, LPR, VPL, U, false, PERM>;
