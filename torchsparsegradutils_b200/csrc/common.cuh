@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/tsgu_b200.h"
 
@@ -140,6 +141,44 @@ __device__ __forceinline__ T shfl_x(unsigned mask, T v, int lanemask) {
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// L2 capacity of the current device (126 MB on B200), queried once per process.
+inline int64_t l2_bytes() {
+  static int64_t cached = 0;
+  if (cached == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev) == cudaSuccess && v > 0)
+      cached = v;
+    else
+      cached = 96ll << 20;
+  }
+  return cached;
+}
+
+// K-slicing for L2 residency.  When one item of the dense operand (rows x K) does not fit L2, every
+// gathered row is an HBM access and the kernel runs at HBM-gather speed (config 5: 6.5 TB/s).  Cutting K
+// into slices whose rows x Ks footprint fits L2 and running the slices as back-to-back launches turns
+// the re-reads of a row (once per nonzero of that column) into L2 hits; the sparse structure is re-read
+// once per slice, which is small next to the dense traffic.  Returns Ks (== K: do not slice).
+inline int64_t pick_k_slice(int64_t rows, int64_t K, int elem_bytes) {
+  const int64_t l2 = l2_bytes();
+  const int64_t epv = 16 / elem_bytes;
+  static double frac = 0.0;  // share of L2 one slice may occupy (env TSGU_L2_SLICE_FRAC; <= 0 disables slicing)
+  if (frac == 0.0) {
+    const char* e = getenv("TSGU_L2_SLICE_FRAC");
+    frac = e ? atof(e) : 0.0;  // off by default: helps regular rows (config 5 fwd 0.65 -> 0.49 ms at 0.55) but the
+                               // shorter per-slice groups make ragged (transposed) rows 1.6x slower; see DESIGN.md
+    if (frac <= 0.0) frac = -1.0;
+  }
+  if (frac < 0.0 || rows * K * elem_bytes <= (l2 * 3) / 5) return K;
+  for (int64_t parts = 2; parts <= 64; parts *= 2) {
+    if (K % parts) break;
+    const int64_t ks = K / parts;
+    if (ks % (4 * epv)) break;  // keep at least 4 lanes x 16 B per row segment
+    if ((double)(rows * ks * elem_bytes) <= frac * (double)l2) return ks;
+  }
+  return K;
+}
 
 }  // namespace tsgu
 

@@ -23,6 +23,7 @@ struct SddmmParams {
   int64_t batch, n, K;
   int64_t rowptr_bstride, nnz_bstride;
   int64_t g_bs, g_rs, g_cs, b_bs, b_rs, b_cs;
+  int accumulate;  // tile kernel: out[dst] += dot (K processed in L2-sized slices)
 };
 
 // Reduce NB per-lane partials across the LPR lanes of a group with a halving butterfly.
@@ -299,7 +300,11 @@ __global__ void __launch_bounds__(256, TSGU_TILE_MINB) sddmm_tile_kernel(const S
               const int64_t eo = base + slot;
               int64_t dst = eo;
               if (p.out_index) dst = (int64_t)__ldg(p.out_index + eo);
-              if (dst >= 0) p.out[dst] = VT<V>::from_acc(part[i]);
+              if (dst >= 0) {
+                Acc r = part[i];
+                if (p.accumulate) r += VT<V>::to_acc(p.out[dst]);
+                p.out[dst] = VT<V>::from_acc(r);
+              }
             }
           }
         }
@@ -338,6 +343,28 @@ static int launch_sddmm_tile(const SddmmParams<V, I>& p, int64_t nnz_total, cuda
 }
 
 template <typename V, typename I>
+static int sddmm_tile_dispatch(const SddmmParams<V, I>& p, int64_t nnz_total, cudaStream_t s) {
+  constexpr int EPVF = 16 / sizeof(V);
+  const int64_t kv = p.K / EPVF;
+  if (kv <= 4) return launch_sddmm_tile<V, I, 4, 1>(p, nnz_total, s);
+  if (kv <= 8) return launch_sddmm_tile<V, I, 8, 1>(p, nnz_total, s);
+#if TSGU_LPR_CAP == 8
+  if (kv <= 16) return launch_sddmm_tile<V, I, 8, 2>(p, nnz_total, s);
+  if (kv <= 32) return launch_sddmm_tile<V, I, 8, 4>(p, nnz_total, s);
+  if (kv <= 64) return launch_sddmm_tile<V, I, 16, 4>(p, nnz_total, s);
+#elif TSGU_LPR_CAP == 16
+  if (kv <= 16) return launch_sddmm_tile<V, I, 16, 1>(p, nnz_total, s);
+  if (kv <= 32) return launch_sddmm_tile<V, I, 16, 2>(p, nnz_total, s);
+  if (kv <= 64) return launch_sddmm_tile<V, I, 16, 4>(p, nnz_total, s);
+#else
+  if (kv <= 16) return launch_sddmm_tile<V, I, 16, 1>(p, nnz_total, s);
+  if (kv <= 32) return launch_sddmm_tile<V, I, 32, 1>(p, nnz_total, s);
+  if (kv <= 64) return launch_sddmm_tile<V, I, 32, 2>(p, nnz_total, s);
+#endif
+  return launch_sddmm_tile<V, I, 32, 4>(p, nnz_total, s);
+}
+
+template <typename V, typename I>
 static int sddmm_dispatch(const SddmmParams<V, I>& p, int64_t m, int64_t nnz_total, int algo, void* ws, size_t ws_bytes,
                           cudaStream_t s) {
   constexpr int EPVF = 16 / sizeof(V);
@@ -351,23 +378,21 @@ static int sddmm_dispatch(const SddmmParams<V, I>& p, int64_t m, int64_t nnz_tot
                                       ws, ws_bytes, s);
   const bool tiny = p.batch * p.n < 64 * 2 * kNumSMs;  // fewer rows than ~64 per resident CTA
   if (fast_ok && algo != TSGU_ALGO_ROWSPLIT && !tiny) {
-    const int64_t kv = p.K / EPVF;
-    if (kv <= 4) return launch_sddmm_tile<V, I, 4, 1>(p, nnz_total, s);
-    if (kv <= 8) return launch_sddmm_tile<V, I, 8, 1>(p, nnz_total, s);
-#if TSGU_LPR_CAP == 8
-    if (kv <= 16) return launch_sddmm_tile<V, I, 8, 2>(p, nnz_total, s);
-    if (kv <= 32) return launch_sddmm_tile<V, I, 8, 4>(p, nnz_total, s);
-    if (kv <= 64) return launch_sddmm_tile<V, I, 16, 4>(p, nnz_total, s);
-#elif TSGU_LPR_CAP == 16
-    if (kv <= 16) return launch_sddmm_tile<V, I, 16, 1>(p, nnz_total, s);
-    if (kv <= 32) return launch_sddmm_tile<V, I, 16, 2>(p, nnz_total, s);
-    if (kv <= 64) return launch_sddmm_tile<V, I, 16, 4>(p, nnz_total, s);
-#else
-    if (kv <= 16) return launch_sddmm_tile<V, I, 16, 1>(p, nnz_total, s);
-    if (kv <= 32) return launch_sddmm_tile<V, I, 32, 1>(p, nnz_total, s);
-    if (kv <= 64) return launch_sddmm_tile<V, I, 32, 2>(p, nnz_total, s);
-#endif
-    return launch_sddmm_tile<V, I, 32, 4>(p, nnz_total, s);
+    // L2 blocking (see pick_k_slice): partial dots of the K slices are accumulated into `out`
+    const int64_t ks = pick_k_slice(m, p.K, (int)sizeof(V));
+    if (ks < p.K && sizeof(V) >= 4) {  // bf16 would round the running sum at every slice: not sliced
+      for (int64_t k0 = 0; k0 < p.K; k0 += ks) {
+        SddmmParams<V, I> q = p;
+        q.B = p.B + k0;
+        q.G = p.G + k0;
+        q.K = ks;
+        q.accumulate = k0 > 0;
+        const int rc = sddmm_tile_dispatch<V, I>(q, nnz_total, s);
+        if (rc) return rc;
+      }
+      return 0;
+    }
+    return sddmm_tile_dispatch<V, I>(p, nnz_total, s);
   }
   if (vec_ok) {
     const int64_t kv = p.K / EPVF;
@@ -469,6 +494,7 @@ extern "C" int tsgu_sddmm_csr(const void* rowptr, const void* colind, const void
     p.batch = batch; p.n = n; p.K = K;
     p.rowptr_bstride = rowptr_bstride; p.nnz_bstride = nnz_bstride;
     p.g_bs = g_bs; p.g_rs = g_rs; p.g_cs = g_cs; p.b_bs = b_bs; p.b_rs = b_rs; p.b_cs = b_cs;
+    p.accumulate = 0;
     return tsgu::sddmm_dispatch<V, I>(p, m, nnz_total, algo, workspace, workspace_bytes, tsgu::as_stream(stream));
   }));
   return 0;

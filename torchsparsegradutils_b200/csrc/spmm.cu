@@ -316,6 +316,33 @@ static int launch_tile(const SpmmParams<V, I>& p, int64_t nnz_total, cudaStream_
 }
 
 template <typename V, typename I>
+static int spmm_tile_dispatch(const SpmmParams<V, I>& p, int64_t nnz_total, cudaStream_t s) {
+  constexpr int EPVF = 16 / sizeof(V);
+  const int64_t kv = p.K / EPVF;
+#define TSGU_TILE(LPR_, VPL_) \
+  return p.perm ? launch_tile<V, I, LPR_, VPL_, true>(p, nnz_total, s) : launch_tile<V, I, LPR_, VPL_, false>(p, nnz_total, s)
+  // narrower lane groups with more vectors per lane serve several rows per warp instruction, which
+  // divides the shuffle (col / val broadcast) traffic on the LSU return path (TSGU_LPR_CAP, tile.cuh)
+  if (kv <= 4) TSGU_TILE(4, 1);
+  if (kv <= 8) TSGU_TILE(8, 1);
+#if TSGU_LPR_CAP == 8
+  if (kv <= 16) TSGU_TILE(8, 2);
+  if (kv <= 32) TSGU_TILE(8, 4);
+  if (kv <= 64) TSGU_TILE(16, 4);
+#elif TSGU_LPR_CAP == 16
+  if (kv <= 16) TSGU_TILE(16, 1);
+  if (kv <= 32) TSGU_TILE(16, 2);
+  if (kv <= 64) TSGU_TILE(16, 4);
+#else
+  if (kv <= 16) TSGU_TILE(16, 1);
+  if (kv <= 32) TSGU_TILE(32, 1);
+  if (kv <= 64) TSGU_TILE(32, 2);
+#endif
+  TSGU_TILE(32, 4);
+#undef TSGU_TILE
+}
+
+template <typename V, typename I>
 static int spmm_dispatch(const SpmmParams<V, I>& p, int64_t m, int64_t nnz_total, int algo, void* ws, size_t ws_bytes,
                          cudaStream_t s) {
   constexpr int EPVF = 16 / sizeof(V);
@@ -329,28 +356,20 @@ static int spmm_dispatch(const SpmmParams<V, I>& p, int64_t m, int64_t nnz_total
   // small problems cannot fill 148 SMs with 64-row tiles: one row per lane group, one CTA per 256/LPR rows
   const bool tiny = p.batch * p.n < 64 * 2 * kNumSMs;  // fewer rows than ~64 per resident CTA
   if (fast_ok && algo != TSGU_ALGO_ROWSPLIT && !tiny) {
-    const int64_t kv = p.K / EPVF;
-#define TSGU_TILE(LPR_, VPL_) \
-  return p.perm ? launch_tile<V, I, LPR_, VPL_, true>(p, nnz_total, s) : launch_tile<V, I, LPR_, VPL_, false>(p, nnz_total, s)
-    // narrower lane groups with more vectors per lane serve several rows per warp instruction, which
-    // divides the shuffle (col / val broadcast) traffic on the LSU return path (TSGU_LPR_CAP, tile.cuh)
-    if (kv <= 4) TSGU_TILE(4, 1);
-    if (kv <= 8) TSGU_TILE(8, 1);
-#if TSGU_LPR_CAP == 8
-    if (kv <= 16) TSGU_TILE(8, 2);
-    if (kv <= 32) TSGU_TILE(8, 4);
-    if (kv <= 64) TSGU_TILE(16, 4);
-#elif TSGU_LPR_CAP == 16
-    if (kv <= 16) TSGU_TILE(16, 1);
-    if (kv <= 32) TSGU_TILE(16, 2);
-    if (kv <= 64) TSGU_TILE(16, 4);
-#else
-    if (kv <= 16) TSGU_TILE(16, 1);
-    if (kv <= 32) TSGU_TILE(32, 1);
-    if (kv <= 64) TSGU_TILE(32, 2);
-#endif
-    TSGU_TILE(32, 4);
-#undef TSGU_TILE
+    // L2 blocking: run K in slices whose dense footprint stays L2-resident (see pick_k_slice)
+    const int64_t ks = pick_k_slice(m, p.K, (int)sizeof(V));
+    if (ks < p.K) {
+      for (int64_t k0 = 0; k0 < p.K; k0 += ks) {
+        SpmmParams<V, I> q = p;
+        q.B = p.B + k0;
+        q.C = p.C + k0;
+        q.K = ks;
+        const int rc = spmm_tile_dispatch<V, I>(q, nnz_total, s);
+        if (rc) return rc;
+      }
+      return 0;
+    }
+    return spmm_tile_dispatch<V, I>(p, nnz_total, s);
   }
   if (vec_ok) {
     const int64_t kv = p.K / EPVF;  // vectors per row
