@@ -414,3 +414,41 @@ def test_merge_path_coo_unsorted(monkeypatch):
     A = torch.sparse_coo_tensor(torch.stack([rows, col])[:, sh], vals[sh], (700, 5000))
     _check(A, torch.rand(5000, 32, device=DEV), torch.rand(700, 32, device=DEV))
     tsgu.clear_pattern_cache()
+
+
+# ------------------------------------------------------------------ remaining C-ABI entry points
+@pytest.mark.parametrize("K", [1, 5, 32, 64, 256, 1100])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.bfloat16])
+def test_sddmm_coo_entry_point(K, dtype):
+    """tsgu_sddmm_coo: order-agnostic <G[row], B[col]> on raw int64 COO coordinates (the idiom the
+    solve / lstsq backwards share, sparse_solve.py:216-235) vs the oracle."""
+    from torchsparsegradutils_b200 import _ops
+
+    n, m, nnz = 150, 90, 2000
+    g = torch.Generator().manual_seed(K)
+    row = torch.randint(0, n, (nnz,), generator=g).to(DEV)
+    col = torch.randint(0, m, (nnz,), generator=g).to(DEV)
+    G = torch.rand(n, K, generator=g).to(dtype).to(DEV)
+    B = torch.rand(m, K, generator=g).to(dtype).to(DEV)
+    out = _ops.sddmm_coo(row, col, G, B)
+    odt = np.float64 if dtype == torch.float64 else np.float32
+    ref = orc.sddmm(_np(row), _np(col), _np(G).astype(odt), _np(B).astype(odt))
+    torch.testing.assert_close(out.double().cpu(), torch.from_numpy(ref.astype(np.float64)), **TOL[dtype])
+    # strided operands take the scalar path
+    out_t = _ops.sddmm_coo(row, col, G.t().contiguous().t(), B)
+    torch.testing.assert_close(out_t, out, **TOL[dtype])
+
+
+@pytest.mark.parametrize("shape", [(1, 1000, 7), (3, 257, 33), (2, 64, 128), (1, 5, 1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.bfloat16])
+def test_copy_dense_layouts(shape, dtype):
+    """tsgu_pack_dense between every pair of (row-major, column-major, batch-last) layouts."""
+    from torchsparsegradutils_b200 import _ops
+
+    x = torch.randn(shape, device=DEV).to(dtype)
+    views = [x, x.transpose(1, 2).contiguous().transpose(1, 2), x.permute(1, 2, 0).contiguous().permute(2, 0, 1)]
+    for src in views:
+        assert torch.equal(_ops.pack_dense(src), x)
+        for like in views:
+            out = _ops.restride_like(src, src.shape, like.stride())
+            assert out.stride() == like.stride() and torch.equal(out, x)
