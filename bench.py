@@ -189,6 +189,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="batched configs at N > 1: weak = every rank runs the full batch (global batch = batch x N); "
+                         "strong = the batch items are split over the ranks")
+    ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (launch-bound cases)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
@@ -225,13 +229,21 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
+    scaling = "strong"
+    shard, seed_shift = None, 0
     if cfg.get("batch") and world > 1:
-        assert cfg["batch"] % world == 0, "batch must divide across ranks"
-        per = cfg["batch"] // world
-        shard = (rank * per, (rank + 1) * per)
-    else:
-        shard = None
-    A, B, G = build_inputs(cfg, dev, shard)
+        if args.scaling == "strong":  # BASELINE's literal reading: batch 8 split over the ranks
+            assert cfg["batch"] % world == 0, "batch must divide across ranks"
+            per = cfg["batch"] // world
+            shard = (rank * per, (rank + 1) * per)
+            config_out["sharding"] = f"strong: {cfg['batch']} batch items split over {world} ranks, no collective"
+        else:  # independent batch items: every rank owns a full batch of its own (weak scaling)
+            scaling, seed_shift = "weak", 1000 * rank
+            config_out["sharding"] = (f"weak: {cfg['batch']} batch items per rank, global batch {cfg['batch'] * world}, "
+                                      "no collective")
+    elif world == 1:
+        scaling = args.scaling if cfg.get("batch") else "strong"
+    A, B, G = build_inputs(cfg, dev, shard, seed_shift)
     row_sharded = world > 1 and not cfg.get("batch") and A.layout == torch.sparse_csr
     if row_sharded:
         # one large matrix: nnz-balanced row blocks, B replicated, grad_B all-reduced over NVLink
@@ -261,16 +273,39 @@ def main():
     for _ in range(warmup):
         step()
     barrier()
+    run_step = step
+    if args.graph:  # capture one steady-state step (pattern cache warm) and replay it
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        cap0 = nat.launch_count()
+        with torch.cuda.graph(graph):
+            step()
+        graph_launches = nat.launch_count() - cap0  # kernels of ours inside one replay
+        run_step = graph.replay
+        config_out["cuda_graph"] = True
+        barrier()
     launches0 = nat.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk, _ops.KernelTimer() as kt:
         e0.record()
         for _ in range(args.steps):
-            step()
+            run_step()
         e1.record()
         barrier()
     ms_total = e0.elapsed_time(e1)
     launches = nat.launch_count() - launches0
+    if args.graph:
+        launches = graph_launches * args.steps
+        with _ops.KernelTimer() as kt:  # per-kernel durations cannot be read out of a graph replay: eager pass
+            for _ in range(5):
+                step()
+            torch.cuda.synchronize()
+        config_out["kernel_times"] = "separate eager pass of 5 steps (graph replays are opaque to events)"
     if dist is not None:
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -326,7 +361,7 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
                 "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic", "config": config_out,
                 "clocks": clk.report(), "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline,
                 "cpu_baseline": cpu_base, "gflops": st["flops"] * (nnz_all / st["nnz"]) / (ms_step * 1e-3) / 1e9,

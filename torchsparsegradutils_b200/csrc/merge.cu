@@ -15,6 +15,15 @@
 #ifndef TSGU_MERGE_P
 #define TSGU_MERGE_P 2048
 #endif
+#ifndef TSGU_MERGE_MINB
+#define TSGU_MERGE_MINB 3   // resident CTAs per SM the register allocation aims for (swept on config 4)
+#endif
+#ifndef TSGU_MERGE_SDDMM_MINB
+#define TSGU_MERGE_SDDMM_MINB 4
+#endif
+#ifndef TSGU_MERGE_LOADS
+#define TSGU_MERGE_LOADS 8   // 128-bit dense-row loads in flight per lane
+#endif
 
 namespace tsgu {
 
@@ -115,7 +124,7 @@ struct MergeSpmmParams {
 
 // =========================================================================================== SpMM
 template <typename V, typename I, int LPR, int VPL, int U, bool EXACT, bool PERM>
-__global__ void __launch_bounds__(256, 2) spmm_merge_kernel(const MergeSpmmParams<V, I> p, const int64_t num_tiles) {
+__global__ void __launch_bounds__(256, TSGU_MERGE_MINB) spmm_merge_kernel(const MergeSpmmParams<V, I> p, const int64_t num_tiles) {
   using Acc = typename VT<V>::Acc;
   using Stage = MergeStage<V, I, PERM ? 2 : 1>;
   constexpr int EPV = 16 / sizeof(V);
@@ -373,7 +382,7 @@ static int launch_spmm_merge(const I* rowptr, const I* colind, const V* vals, co
                              cudaStream_t s) {
   using Acc = typename VT<V>::Acc;
   constexpr int EPV = 16 / sizeof(V);
-  constexpr int U0 = TSGU_TILE_LOADS / VPL;
+  constexpr int U0 = TSGU_MERGE_LOADS / VPL;
   constexpr int U = U0 < LPR ? U0 : LPR;
   const int64_t num_tiles = (rows + nnz + MERGE_P - 1) / MERGE_P;
   const int64_t kpad = (int64_t)LPR * VPL * EPV;
@@ -493,7 +502,7 @@ struct MergeSddmmSmem {
 };
 
 template <typename V, typename I, int LPR, int VPL, int NB, int U, bool EXACT>
-__global__ void __launch_bounds__(256, 2) sddmm_merge_kernel(const MergeSddmmParams<V, I> p, const int64_t num_tiles) {
+__global__ void __launch_bounds__(256, TSGU_MERGE_SDDMM_MINB) sddmm_merge_kernel(const MergeSddmmParams<V, I> p, const int64_t num_tiles) {
   using Acc = typename VT<V>::Acc;
   using Stage = MergeStage<V, I, 0>;
   using Smem = MergeSddmmSmem<V, I>;
@@ -641,7 +650,7 @@ template <typename V, typename I, int LPR, int VPL>
 static int launch_sddmm_merge(const MergeSddmmParams<V, I>& p0, void* ws, size_t ws_bytes, cudaStream_t s) {
   constexpr int EPV = 16 / sizeof(V);
   constexpr int NB = LPR < 16 ? LPR : 16;
-  constexpr int U0 = TSGU_TILE_LOADS / VPL;
+  constexpr int U0 = TSGU_MERGE_LOADS / VPL;
   constexpr int U = U0 < NB ? U0 : NB;
   MergeSddmmParams<V, I> p = p0;
   const int64_t num_tiles = (p.rows + p.nnz + MERGE_P - 1) / MERGE_P;
