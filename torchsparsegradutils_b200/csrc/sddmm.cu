@@ -147,7 +147,7 @@ static int launch_sddmm(const SddmmParams<V, I>& p, cudaStream_t s) {
 // Fast path: persistent row-tile kernel; rowptr / colind staged by the bulk-copy engine (tile.cuh).
 // =============================================================================================
 template <typename V, typename I, int LPR, int VPL, int NB, int U, bool EXACT>
-__global__ void __launch_bounds__(256, TSGU_TILE_MINB) sddmm_tile_kernel(const SddmmParams<V, I> p, const int64_t tiles_per_item,
+__global__ void __launch_bounds__(256, TSGU_TILE_MINB(VPL)) sddmm_tile_kernel(const SddmmParams<V, I> p, const int64_t tiles_per_item,
                                                             const int64_t num_tiles, const int64_t rowptr_len,
                                                             const int64_t nnz_len, const int tile_rows) {
   using Acc = typename VT<V>::Acc;
@@ -318,7 +318,7 @@ template <typename V, typename I, int LPR, int VPL>
 static int launch_sddmm_tile(const SddmmParams<V, I>& p, int64_t nnz_total, cudaStream_t s) {
   using Cfg = TileCfg<V, I, 0>;
   constexpr int NB = 16;  // entries per batch (butterfly leaves NB/LPR results per lane when NB > LPR)
-  constexpr int U0 = TSGU_TILE_LOADS / VPL;
+  constexpr int U0 = TSGU_TILE_LOADS(VPL) / VPL;
   constexpr int U = U0 < NB ? U0 : NB;
   constexpr int EPV = 16 / sizeof(V);
   const bool exact = (p.K / EPV) == (int64_t)LPR * VPL;

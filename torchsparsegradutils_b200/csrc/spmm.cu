@@ -126,7 +126,7 @@ static int launch_rowsplit(const SpmmParams<V, I>& p, cudaStream_t s) {
 // permutation, K <= 32*4 vectors, m < 2^32.
 // =============================================================================================
 template <typename V, typename I, int LPR, int VPL, int U, bool EXACT, bool PERM>
-__global__ void __launch_bounds__(256, TSGU_TILE_MINB) spmm_tile_kernel(const SpmmParams<V, I> p, const int64_t tiles_per_item,
+__global__ void __launch_bounds__(256, TSGU_TILE_MINB(VPL)) spmm_tile_kernel(const SpmmParams<V, I> p, const int64_t tiles_per_item,
                                                         const int64_t num_tiles, const int64_t rowptr_len,
                                                         const int64_t nnz_len, const int tile_rows) {
   using Acc = typename VT<V>::Acc;
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(256, TSGU_TILE_MINB) spmm_tile_kernel(const Sp
 template <typename V, typename I, int LPR, int VPL, bool PERM>
 static int launch_tile(const SpmmParams<V, I>& p, int64_t nnz_total, cudaStream_t s) {
   using Cfg = TileCfg<V, I, PERM ? 2 : 1>;
-  constexpr int U0 = TSGU_TILE_LOADS / VPL;  // independent 128-bit loads in flight per lane ...
+  constexpr int U0 = TSGU_TILE_LOADS(VPL) / VPL;  // independent 128-bit loads in flight per lane ...
   constexpr int U = U0 < 32 ? U0 : 32;        // ... (a batch is 32 entries)
   constexpr int EPV = 16 / sizeof(V);
   const bool exact = (p.K / EPV) == (int64_t)LPR * VPL;

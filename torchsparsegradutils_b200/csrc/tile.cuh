@@ -9,12 +9,16 @@
 #pragma once
 #include "common.cuh"
 
-// tunables (overridable at build time for experiments: TSGU_EXTRA_NVCC_FLAGS="-DTSGU_TILE_MINB=2 ...")
+// tunables (overridable at build time for experiments: TSGU_EXTRA_NVCC_FLAGS='-DTSGU_TILE_MINB(VPL)=2 ...')
+// (resident CTAs per SM the register allocation aims for, 128-bit dense-row loads in flight per lane
+// before the FMA chain) as a function of the vectors per lane; swept on the box: one vector per lane
+// (K*s_v <= 128 B, config 3) wants more warps and shorter bursts, four vectors per lane (configs 2, 5)
+// the opposite
 #ifndef TSGU_TILE_MINB
-#define TSGU_TILE_MINB 2    // resident CTAs per SM the register allocation aims for
+#define TSGU_TILE_MINB(VPL) ((VPL) == 1 ? 3 : 2)
 #endif
 #ifndef TSGU_TILE_LOADS
-#define TSGU_TILE_LOADS 16  // 128-bit dense-row loads in flight per lane before the FMA chain
+#define TSGU_TILE_LOADS(VPL) ((VPL) == 1 ? 8 : 16)
 #endif
 #ifndef TSGU_LPR_CAP
 #define TSGU_LPR_CAP 8     // widest lane group the tile kernels use (8 / 16 / 32)
