@@ -77,9 +77,15 @@ def test_config2_full_size_properties():
                        torch.randint(0, 65536, (16,), generator=g), tol)
 
 
-def test_config2_transpose_structure_full_size():
+def test_config2_transpose_structure_full_size(monkeypatch):
+    import torchsparsegradutils_b200 as tsgu
+    from torchsparsegradutils_b200 import _pattern
     from torchsparsegradutils_b200._pattern import csr_pattern
 
+    # the exact structure A.t().to_sparse_csr() would give: row padding (a layout optimisation of the
+    # cached transpose, covered by test_padded_transpose_is_equivalent) is switched off here
+    monkeypatch.setattr(_pattern, "_PAD_MIN_NNZ", 1 << 62)
+    tsgu.clear_pattern_cache()
     A = W.uniform_rows_csr(8, 65536, 65536, 16, torch.float32, torch.int32, DEV, seed=2)
     P = csr_pattern(A)
     T = P.transpose()
@@ -101,6 +107,27 @@ def test_config2_transpose_structure_full_size():
     assert torch.equal(TT.rowptr.long(), flat_crow)
     assert torch.equal(TT.colind.long(), cols_of_A)
     assert torch.equal(TT.perm.long(), torch.arange(nnz, device=DEV))
+
+
+def test_padded_transpose_is_equivalent(monkeypatch):
+    """Rows of the cached transpose are padded to multiples of 4 with explicit zeros: same grad_B, bit for bit."""
+    import torchsparsegradutils_b200 as tsgu
+    from torchsparsegradutils_b200 import _pattern
+    from torchsparsegradutils_b200._pattern import csr_pattern
+
+    tsgu.clear_pattern_cache()
+    A = W.uniform_rows_csr(2, 65536, 65536, 16, torch.float32, torch.int32, DEV, seed=7)
+    B, G = W.dense_operands((2, 65536, 65536), 128, torch.float32, DEV, seed=8)
+    T = csr_pattern(A).transpose()
+    lens = T.rowptr[1:] - T.rowptr[:-1]
+    assert bool((lens % 4 == 0).all()) and T.nnz_total > 2 * 65536 * 16 and int((T.perm < 0).sum()) == T.nnz_total - 2 * 65536 * 16
+    _, _, gB_pad = _fwd_bwd(A, B, G)
+    monkeypatch.setattr(_pattern, "_PAD_MIN_NNZ", 1 << 62)
+    tsgu.clear_pattern_cache()
+    assert csr_pattern(A).transpose().nnz_total == 2 * 65536 * 16
+    _, _, gB_ref = _fwd_bwd(A, B, G)
+    tsgu.clear_pattern_cache()
+    assert torch.equal(gB_pad, gB_ref)
 
 
 def test_config5_long_k_properties():

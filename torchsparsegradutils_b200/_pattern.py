@@ -119,8 +119,41 @@ def _build_transpose(p: CsrPattern) -> CsrPattern:
     if p.perm is not None and p.nnz_total > 0:
         # entries of p are themselves a permutation of the caller's value storage: compose once
         permT = p.perm.to(odt).index_select(0, permT.long()) if p.perm.dtype != odt else p.perm.index_select(0, permT.long())
-    return CsrPattern(rowptrT, colindT, permT, p.batch, p.m, p.n, p.m, 0, p.nnz_total, out_idx,
-                      algo=choose_algo(rowptrT, p.batch, p.m, p.nnz_total), keep=(p,))
+    algo = choose_algo(rowptrT, p.batch, p.m, p.nnz_total)
+    nnzT = p.nnz_total
+    if algo != nat.ALGO_MERGE and nnzT >= _PAD_MIN_NNZ:
+        rowptrT, colindT, permT, nnzT = _pad_rows(rowptrT, colindT, permT, _ROW_PAD)
+    return CsrPattern(rowptrT, colindT, permT, p.batch, p.m, p.n, p.m, 0, nnzT, out_idx, algo=algo, keep=(p,))
+
+
+_ROW_PAD = 4          # the row-split kernels consume a row in groups of >= 4 entries
+_PAD_MIN_NNZ = 1 << 18
+
+
+def _pad_rows(rowptr: torch.Tensor, colind: torch.Tensor, perm: torch.Tensor, mult: int):
+    """Pad every row of a structure WE own (a transpose) to a multiple of `mult` entries.
+
+    Rows of a transposed matrix have Poisson-like lengths, so most rows end in a partly filled group of
+    gathers; that ragged path costs the transposed SpMM 20-60 % (profiles/r1_gather_ceilings.txt).
+    Padding entries repeat the row's last column (an L1-hot dense row) and carry perm = -1, which the
+    value gather turns into an explicit 0, so the product is unchanged.  One-off, cached with the pattern.
+    """
+    lens = (rowptr[1:] - rowptr[:-1]).long()
+    plen = (lens + (mult - 1)) // mult * mult
+    if bool((plen == lens).all()):
+        return rowptr, colind, perm, colind.numel()
+    rows = lens.numel()
+    new_rowptr = torch.zeros(rows + 1, dtype=torch.int64, device=rowptr.device)
+    new_rowptr[1:] = plen.cumsum(0)
+    total = int(new_rowptr[-1])
+    row_of = torch.repeat_interleave(torch.arange(rows, device=rowptr.device), lens)
+    new_pos = new_rowptr[row_of] + (torch.arange(colind.numel(), device=rowptr.device) - rowptr.long()[row_of])
+    last_col = colind[(rowptr[1:].long() - 1).clamp_(min=0)]  # unused for empty rows (plen == 0)
+    colind_p = torch.repeat_interleave(last_col, plen)
+    colind_p[new_pos] = colind
+    perm_p = torch.full((total,), -1, dtype=perm.dtype, device=perm.device)
+    perm_p[new_pos] = perm
+    return new_rowptr.to(rowptr.dtype), colind_p, perm_p, total
 
 
 def _cache_get(key):

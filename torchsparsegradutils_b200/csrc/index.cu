@@ -234,7 +234,10 @@ template <typename V, typename I>
 __global__ void gather_values_kernel(const V* __restrict__ in, const I* __restrict__ perm, V* __restrict__ out,
                                      int64_t count) {
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (int64_t)gridDim.x * blockDim.x)
-    out[k] = in[(int64_t)perm[k]];
+  {
+    const int64_t src = (int64_t)perm[k];
+    out[k] = src >= 0 ? in[src] : VT<V>::from_acc(0);  // perm < 0: explicit zero (padding entry of a transposed structure)
+  }
 }
 
 template <typename V, typename I>
