@@ -293,8 +293,10 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk, _ops.KernelTimer() as kt:
         e0.record()
+        t_host = time.perf_counter()
         for _ in range(args.steps):
             run_step()
+        host_ms = (time.perf_counter() - t_host) * 1e3 / args.steps  # time to ENQUEUE a step (no sync)
         e1.record()
         barrier()
     ms_total = e0.elapsed_time(e1)
@@ -366,7 +368,8 @@ def main():
                 "clocks": clk.report(), "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline,
                 "cpu_baseline": cpu_base, "gflops": st["flops"] * (nnz_all / st["nnz"]) / (ms_step * 1e-3) / 1e9,
                 "step_alg_gbs": step_gbs * (nnz_all / st["nnz"]), "step_frac_of_hbm_peak": step_gbs / peak,
-                "kernels": kernels, "nnz_per_step": nnz_all}
+                "kernels": kernels, "nnz_per_step": nnz_all,
+                "host_enqueue_ms_per_step": host_ms}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
