@@ -21,6 +21,9 @@
 #ifndef TSGU_MERGE_SDDMM_MINB
 #define TSGU_MERGE_SDDMM_MINB 4
 #endif
+#ifndef TSGU_MERGE_NARROW
+#define TSGU_MERGE_NARROW 1  // 8-lane groups with 2-4 vectors per lane, as the tile kernels (config 4: 9.7 -> 9.2 ms)
+#endif
 #ifndef TSGU_MERGE_LOADS
 #define TSGU_MERGE_LOADS 8   // 128-bit dense-row loads in flight per lane
 #endif
@@ -424,7 +427,7 @@ size_t spmm_merge_workspace_bytes(int64_t rows, int64_t K, int64_t nnz, int val_
   const int asz = val_dtype == TSGU_F64 ? 8 : 4;
   const int epv = 16 / esz;
   int64_t kv = (K + epv - 1) / epv;  // vectors per row -> lane tiling used by the dispatcher
-  int64_t slots = kv <= 4 ? 4 : kv <= 8 ? 8 : kv <= 16 ? 16 : kv <= 32 ? 32 : kv <= 64 ? 64 : 128;
+  int64_t slots = kv <= 4 ? 4 : kv <= 8 ? 8 : kv <= 16 ? 16 : kv <= 32 ? 32 : kv <= 64 ? 64 : 128;  // = LPR*VPL in both lane tables
   const int64_t kpad = slots * epv;
   const size_t part_bytes = ((size_t)(num_tiles + 1) * 2 * sizeof(int64_t) + 255) / 256 * 256;
   const size_t row_bytes = ((size_t)num_tiles * 2 * sizeof(int64_t) + 255) / 256 * 256;
@@ -442,9 +445,15 @@ int spmm_merge_dispatch(const I* rowptr, const I* colind, const V* vals, const I
               : launch_spmm_merge<V, I, LPR_, VPL_, false>(rowptr, colind, vals, perm, B, C, rows, K, nnz, b_rs, ldc, ws, ws_bytes, s)
   if (kv <= 4) TSGU_MERGE(4, 1);
   if (kv <= 8) TSGU_MERGE(8, 1);
+#if TSGU_MERGE_NARROW
+  if (kv <= 16) TSGU_MERGE(8, 2);
+  if (kv <= 32) TSGU_MERGE(8, 4);
+  if (kv <= 64) TSGU_MERGE(16, 4);
+#else
   if (kv <= 16) TSGU_MERGE(16, 1);
   if (kv <= 32) TSGU_MERGE(32, 1);
   if (kv <= 64) TSGU_MERGE(32, 2);
+#endif
   TSGU_MERGE(32, 4);
 #undef TSGU_MERGE
 }
@@ -688,9 +697,15 @@ int sddmm_merge_dispatch(const I* rowptr, const I* colind, const I* out_index, c
   const int64_t kv = K / EPVF;
   if (kv <= 4) return launch_sddmm_merge<V, I, 4, 1>(p, ws, ws_bytes, s);
   if (kv <= 8) return launch_sddmm_merge<V, I, 8, 1>(p, ws, ws_bytes, s);
+#if TSGU_MERGE_NARROW
+  if (kv <= 16) return launch_sddmm_merge<V, I, 8, 2>(p, ws, ws_bytes, s);
+  if (kv <= 32) return launch_sddmm_merge<V, I, 8, 4>(p, ws, ws_bytes, s);
+  if (kv <= 64) return launch_sddmm_merge<V, I, 16, 4>(p, ws, ws_bytes, s);
+#else
   if (kv <= 16) return launch_sddmm_merge<V, I, 16, 1>(p, ws, ws_bytes, s);
   if (kv <= 32) return launch_sddmm_merge<V, I, 32, 1>(p, ws, ws_bytes, s);
   if (kv <= 64) return launch_sddmm_merge<V, I, 32, 2>(p, ws, ws_bytes, s);
+#endif
   return launch_sddmm_merge<V, I, 32, 4>(p, ws, ws_bytes, s);
 }
 
