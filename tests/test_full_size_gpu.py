@@ -53,6 +53,25 @@ def _sampled_exact(A2d, B, G, C, gvals, gB, rows, cols, tol):
         torch.testing.assert_close(gB[j].double(), ref, **tol)
 
 
+def test_config1_full_size_vs_oracle():
+    """COO 4096x4096 at 1 % x dense 4096x64 fp32 (BASELINE configs[0]): small enough for the whole oracle."""
+    import numpy as np
+
+    from oracle import oracle as orc
+
+    A = W.uniform_coo(4096, 4096, 167772, torch.float32, DEV, seed=1)
+    B = torch.rand(4096, 64, device=DEV)
+    G = torch.rand(4096, 64, device=DEV)
+    C, gA, gB = _fwd_bwd(A, B, G)
+    ref = orc.sparse_mm_fwd_bwd("coo", (4096, 4096), B.cpu().numpy(), G.cpu().numpy(),
+                                indices=A._indices().cpu().numpy(), values=A._values().cpu().numpy())
+    tol = dict(rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(C.cpu().numpy(), ref["C"], **tol)
+    np.testing.assert_allclose(gB.cpu().numpy(), ref["gradB"], **tol)
+    np.testing.assert_allclose(gA._values().cpu().numpy(), ref["gradA_values"], **tol)
+    assert torch.equal(gA._indices(), A._indices()) and gA._nnz() == 167772
+
+
 def test_config2_full_size_properties():
     """batched CSR b=8, 65536^2, 16 nnz/row, K=128 fp32 (BASELINE configs[1])."""
     A = W.uniform_rows_csr(8, 65536, 65536, 16, torch.float32, torch.int32, DEV, seed=2)
