@@ -222,6 +222,10 @@ def main():
     from torchsparsegradutils_b200 import _ops, sparse_mm
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    if not os.path.exists(nat.LIB_PATH) and rank == 0:  # normally shipped prebuilt with the snapshot
+        from torchsparsegradutils_b200.csrc.build import build as _build_native
+
+        _build_native(verbose=True)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
