@@ -452,3 +452,37 @@ def test_copy_dense_layouts(shape, dtype):
         for like in views:
             out = _ops.restride_like(src, src.shape, like.stride())
             assert out.stride() == like.stride() and torch.equal(out, x)
+
+
+@pytest.mark.parametrize("layout", ["coo", "csr", "bcsr"])
+def test_public_sddmm_matches_solve_backward_idiom(layout):
+    """sddmm(A, X, Y) == (X.index_select(0,row) * Y.index_select(0,col)).sum(1), the idiom of
+    sparse_solve.py:216-235 / sparse_lstsq.py:239-256, on A's storage order."""
+    from torchsparsegradutils_b200 import sddmm
+
+    n, m, K = 90, 70, 48
+    if layout == "bcsr":
+        A = rand_csr(n, m, 6, batch=3, seed=4)
+        X, Y = torch.rand(3, n, K, device=DEV), torch.rand(3, m, K, device=DEV)
+        out = sddmm(A, X, Y)
+        assert out.shape == A.values().shape
+        for t in range(3):
+            crow, col = A.crow_indices()[t].long(), A.col_indices()[t].long()
+            row = torch.repeat_interleave(torch.arange(n, device=DEV), crow[1:] - crow[:-1])
+            ref = (X[t].double().index_select(0, row) * Y[t].double().index_select(0, col)).sum(1)
+            torch.testing.assert_close(out[t].double(), ref, rtol=1e-5, atol=1e-6)
+        return
+    Acsr = rand_csr(n, m, 6, seed=5, ragged=True)
+    crow, col = Acsr.crow_indices().long(), Acsr.col_indices().long()
+    row = torch.repeat_interleave(torch.arange(n, device=DEV), crow[1:] - crow[:-1])
+    X, Y = torch.rand(n, K, device=DEV), torch.rand(m, K, device=DEV)
+    if layout == "coo":
+        sh = torch.randperm(col.numel(), device=DEV)
+        row, col = row[sh], col[sh]
+        A = torch.sparse_coo_tensor(torch.stack([row, col]), torch.ones(col.numel(), device=DEV), (n, m))
+    else:
+        A = Acsr
+    ref = (X.double().index_select(0, row) * Y.double().index_select(0, col)).sum(1)
+    torch.testing.assert_close(sddmm(A, X, Y).double(), ref, rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError, match="Incompatible shapes"):
+        sddmm(A, X, torch.rand(m, K + 1, device=DEV))

@@ -40,6 +40,26 @@ class KernelTimer:
         return {k: {"ms": v[0] / v[1], "launches": v[1]} for k, v in out.items()}
 
 
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL = _Null()
+
+
+def _on(dev: torch.device):
+    """Device guard only when `dev` is not already current (the guard costs ~10 us of host time per call)."""
+    return _NULL if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+
+
+def _timer(tag: str, dev: torch.device):
+    return _timed(tag, dev) if KernelTimer.active is not None else _NULL
+
+
 class _timed:
     def __init__(self, tag, device):
         self.kt = KernelTimer.active
@@ -73,7 +93,7 @@ def copy_dense(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
     """dst[...] = src[...] for two (batch, rows, K) tensors of any strides, through tsgu_pack_dense."""
     b, r, k = src.shape
     if src.numel():
-        with torch.cuda.device(src.device):
+        with _on(src.device):
             nat.check(nat.lib().tsgu_pack_dense(src.data_ptr(), dst.data_ptr(), b, r, k, *src.stride(), *dst.stride(),
                                                 nat.val_enum(src.dtype), nat.stream_ptr(src.device)), "tsgu_pack_dense")
     return dst
@@ -141,11 +161,11 @@ def spmm(pat: CsrPattern, vals: torch.Tensor, dense: torch.Tensor, algo: Optiona
     if perm is not None and pat.nnz_total >= _PREGATHER_MIN_NNZ:
         # one streaming pass that puts the values in the structure's own order is cheaper than a
         # divergent 4-byte gather per entry inside the bandwidth-critical SpMM (0.37 -> 0.25+0.03 ms on config 2)
-        with _timed(tag + "_gather", dev):
+        with _timer(tag + "_gather", dev):
             vals = gather_values(vals.reshape(-1), perm)
         perm = None
-    with torch.cuda.device(dev), _timed(tag, dev):
-        ws_bytes = L.tsgu_spmm_workspace_bytes(pat.batch, pat.n, K, pat.nnz_total, vdt, algo)
+    with _on(dev), _timer(tag, dev):
+        ws_bytes = L.tsgu_spmm_workspace_bytes(pat.batch, pat.n, K, pat.nnz_total, vdt, algo) if algo == nat.ALGO_MERGE else 0
         ws = nat.workspace(ws_bytes, dev) if ws_bytes else None
         nat.check(L.tsgu_spmm_csr(nat.ptr(pat.rowptr), nat.ptr(pat.colind), nat.ptr(vals), nat.ptr(perm),
                                   dense.data_ptr(), out.data_ptr(), pat.batch, pat.n, pat.m, K,
@@ -167,8 +187,8 @@ def sddmm(pat: CsrPattern, G: torch.Tensor, B: torch.Tensor, out_index: Optional
         return out
     dev = B.device
     L = nat.lib()
-    with torch.cuda.device(dev), _timed("sddmm", dev):
-        ws_bytes = L.tsgu_sddmm_workspace_bytes(pat.batch, pat.n, pat.nnz_total, algo)
+    with _on(dev), _timer("sddmm", dev):
+        ws_bytes = L.tsgu_sddmm_workspace_bytes(pat.batch, pat.n, pat.nnz_total, algo) if algo == nat.ALGO_MERGE else 0
         ws = nat.workspace(ws_bytes, dev) if ws_bytes else None
         nat.check(L.tsgu_sddmm_csr(nat.ptr(pat.rowptr), nat.ptr(pat.colind), nat.ptr(out_index),
                                            G.data_ptr(), B.data_ptr(), out.data_ptr(), pat.batch, pat.n, pat.m,
@@ -189,7 +209,7 @@ def sddmm_coo(row: torch.Tensor, col: torch.Tensor, G: torch.Tensor, B: torch.Te
     if nnz == 0:
         return out
     row, col = row.contiguous(), col.contiguous()
-    with torch.cuda.device(B.device):
+    with _on(B.device):
         nat.check(nat.lib().tsgu_sddmm_coo(row.data_ptr(), col.data_ptr(), G.data_ptr(), B.data_ptr(), out.data_ptr(),
                                            nnz, B.shape[-1], G.stride(0), G.stride(1), B.stride(0), B.stride(1),
                                            nat.val_enum(B.dtype), nat.stream_ptr(B.device)), "tsgu_sddmm_coo")
@@ -199,7 +219,7 @@ def sddmm_coo(row: torch.Tensor, col: torch.Tensor, G: torch.Tensor, B: torch.Te
 def segment_sum_values(vals: torch.Tensor, perm: torch.Tensor, seg: torch.Tensor, nseg: int) -> torch.Tensor:
     out = torch.empty(nseg, dtype=vals.dtype, device=vals.device)
     if nseg:
-        with torch.cuda.device(vals.device):
+        with _on(vals.device):
             nat.check(nat.lib().tsgu_segment_sum_values(vals.data_ptr(), nat.ptr(perm), seg.data_ptr(), out.data_ptr(),
                                                         nseg, nat.val_enum(vals.dtype), nat.idx_enum(seg.dtype),
                                                         nat.stream_ptr(vals.device)), "tsgu_segment_sum_values")
@@ -209,7 +229,7 @@ def segment_sum_values(vals: torch.Tensor, perm: torch.Tensor, seg: torch.Tensor
 def gather_values(vals: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
     out = torch.empty(perm.shape, dtype=vals.dtype, device=vals.device)
     if out.numel():
-        with torch.cuda.device(vals.device):
+        with _on(vals.device):
             nat.check(nat.lib().tsgu_gather_values(vals.data_ptr(), perm.data_ptr(), out.data_ptr(), perm.numel(),
                                                    nat.val_enum(vals.dtype), nat.idx_enum(perm.dtype),
                                                    nat.stream_ptr(vals.device)), "tsgu_gather_values")
