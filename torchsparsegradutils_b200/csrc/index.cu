@@ -230,13 +230,27 @@ static int transpose_impl(const I* rowptr, const I* colind, int64_t batch, int64
 }
 
 // ----------------------------------------------------------------------- value shuffles
+// out[k] = perm[k] >= 0 ? in[perm[k]] : 0.  Four entries per thread: the four gathers are independent,
+// so each thread keeps four L2 requests in flight (the one-entry version was latency bound at 55 us for
+// config 2's 9.2 M entries).
 template <typename V, typename I>
-__global__ void gather_values_kernel(const V* __restrict__ in, const I* __restrict__ perm, V* __restrict__ out,
-                                     int64_t count) {
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (int64_t)gridDim.x * blockDim.x)
-  {
-    const int64_t src = (int64_t)perm[k];
-    out[k] = src >= 0 ? in[src] : VT<V>::from_acc(0);  // perm < 0: explicit zero (padding entry of a transposed structure)
+__global__ void __launch_bounds__(256) gather_values_kernel(const V* __restrict__ in, const I* __restrict__ perm,
+                                                            V* __restrict__ out, int64_t count) {
+  const int64_t quads = count / 4;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (int64_t)gridDim.x * blockDim.x) {
+    int64_t src[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) src[i] = (int64_t)__ldg(perm + 4 * q + i);
+    V v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = src[i] >= 0 ? __ldg(in + src[i]) : VT<V>::from_acc(0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[4 * q + i] = v[i];
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (count & 3)) {  // tail
+    const int64_t k = quads * 4 + threadIdx.x;
+    const int64_t s1 = (int64_t)perm[k];
+    out[k] = s1 >= 0 ? in[s1] : VT<V>::from_acc(0);
   }
 }
 
@@ -439,7 +453,7 @@ extern "C" int tsgu_gather_values(const void* in, const void* perm, void* out, i
   if (count == 0) return 0;
   cudaStream_t s = as_stream(stream);
   TSGU_DISPATCH_VAL(val_dtype, TSGU_DISPATCH_IDX(idx_dtype, {
-    gather_values_kernel<V, I><<<blocks_for(count, 256), 256, 0, s>>>((const V*)in, (const I*)perm, (V*)out, count);
+    gather_values_kernel<V, I><<<blocks_for((count + 3) / 4, 256), 256, 0, s>>>((const V*)in, (const I*)perm, (V*)out, count);
     count_launch();
   }));
   return launch_status();
