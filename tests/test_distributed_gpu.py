@@ -1,0 +1,63 @@
+"""GPU, >= 2 devices (skipped on a single-GPU box): row-sharded sparse_mm with the overlapped grad_B
+all-reduce over NCCL equals the single-GPU result."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import sys
+
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        import workloads as W
+        from torchsparsegradutils_b200 import distributed as D
+        from torchsparsegradutils_b200 import sparse_mm
+
+        A = W.uniform_rows_csr(None, 20000, 3000, 12, torch.float32, torch.int32, dev, seed=9)
+        B, G = W.dense_operands((20000, 3000), 64, torch.float32, dev, seed=10)
+        bounds = D.nnz_balanced_row_blocks(A.crow_indices(), world)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        A_loc = D.shard_rows_csr(A, lo, hi).requires_grad_(True)
+        B_rep = B.clone().requires_grad_(True)
+        C_loc = D.sparse_mm_row_sharded(A_loc, B_rep)
+        C_loc.backward(G[lo:hi])
+        A_full = A.detach().requires_grad_(True)
+        B_full = B.clone().requires_grad_(True)
+        C = sparse_mm(A_full, B_full)
+        C.backward(G)
+        s, e = int(A.crow_indices()[lo]), int(A.crow_indices()[hi])
+        ok = (torch.equal(C_loc, C[lo:hi]) and torch.equal(A_loc.grad.values(), A_full.grad.values()[s:e])
+              and torch.allclose(B_rep.grad, B_full.grad, rtol=1e-5, atol=1e-5))
+        flags = [None] * world
+        dist.all_gather_object(flags, bool(ok))
+        if rank == 0:
+            out.put(all(flags))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_row_sharded_nccl_matches_single_gpu():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert out.get() is True

@@ -21,7 +21,7 @@ from typing import Callable, List, Optional, Tuple
 import torch
 import torch.distributed as dist
 
-from .sparse_matmul import sparse_mm
+from .sparse_matmul import SparseMatMul, _grad_A, _grad_B, sparse_mm
 
 
 # ------------------------------------------------------------------------------ batch sharding
@@ -93,6 +93,27 @@ class _AllReduceGrad(torch.autograd.Function):
         return grad, None
 
 
+class _RowShardedMatMul(torch.autograd.Function):
+    """sparse_mm on this rank's row block with the grad_B all-reduce issued as soon as the local partial
+    exists, so it travels over NVLink while the SDDMM (grad_A, purely local) is still running."""
+
+    @staticmethod
+    def forward(ctx, A_local, B, group):
+        ctx.group = group
+        return SparseMatMul.forward(ctx, A_local, B)
+
+    @staticmethod
+    def backward(ctx, grad):  # type: ignore[override]
+        gradB = work = None
+        if ctx.needs_input_grad[1]:
+            gradB = _grad_B(ctx, grad).contiguous()
+            work = dist.all_reduce(gradB, op=dist.ReduceOp.SUM, group=ctx.group, async_op=True)
+        gradA = _grad_A(ctx, grad) if ctx.needs_input_grad[0] else None
+        if work is not None:
+            work.wait()
+        return gradA, gradB, None
+
+
 def sparse_mm_row_sharded(A_local: torch.Tensor, B: torch.Tensor, group: Optional[dist.ProcessGroup] = None,
                           local_mm: Callable[[torch.Tensor, torch.Tensor], torch.Tensor] = sparse_mm) -> torch.Tensor:
     """C_local = A_local @ B for this rank's row block; B is replicated on every rank.
@@ -100,6 +121,9 @@ def sparse_mm_row_sharded(A_local: torch.Tensor, B: torch.Tensor, group: Optiona
     grad_A_local and C_local stay local; grad_B is all-reduced so every replica of B sees the full
     A^T G (the only collective on the path).
     """
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        B = _AllReduceGrad.apply(B, group)
-    return local_mm(A_local, B)
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if not distributed:
+        return local_mm(A_local, B)
+    if local_mm is sparse_mm:  # product path: collective overlapped with the SDDMM
+        return _RowShardedMatMul.apply(A_local, B, group)
+    return local_mm(A_local, _AllReduceGrad.apply(B, group))

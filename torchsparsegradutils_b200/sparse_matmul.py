@@ -119,40 +119,44 @@ class SparseMatMul(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad):  # type: ignore[override]
-        saved = ctx.saved_tensors
-        A, B = saved[0], saved[1]
-        pat = ctx.pattern
-        is_csr = isinstance(pat, CsrPattern)
-        csr = pat if is_csr else cast(CooPattern, pat).csr
-
-        gradA = None
-        gradB = None
-
-        if ctx.needs_input_grad[0]:
-            # grad_A[e] = <grad[i_e, :], B[j_e, :]> on A's pattern only (reference :173-219)
-            if is_csr:
-                v = _ops.sddmm(csr, grad, B, None, csr.nnz_total)
-                gradA = torch.sparse_csr_tensor(A.crow_indices(), A.col_indices(), v.view(A.values().shape), A.shape)
-            elif not ctx.batched:
-                # per stored entry, in storage order (duplicates each get the full dot product)
-                v = _ops.sddmm(csr, grad, B, pat.out_index, csr.nnz_total)
-                gradA = torch.sparse_coo_tensor(A._indices(), v, A.shape)
-            else:
-                # batched COO: the gradient lives on the sorted unique pattern (reference :213-217)
-                v = _ops.sddmm(csr, grad, B, None, pat.nnz_unique)
-                gradA = torch.sparse_coo_tensor(pat.grad_indices, v, A.shape)
-
-        if ctx.needs_input_grad[1]:
-            # grad_B = A^T grad through the cached transposed structure (reference :222-232)
-            if len(saved) > 2:
-                vals = saved[2]
-            elif is_csr:
-                vals = A.values().contiguous()
-            else:
-                vals = A._values().contiguous()
-            gradB = _ops.spmm(csr.transpose(), vals, grad, tag="spmm_gradB")
-            gradB = gradB if ctx.batched else gradB[0]
-            if ctx.B_strides is not None:
-                gradB = _ops.restride_like(gradB, ctx.B_shape, ctx.B_strides)
-
+        gradA = _grad_A(ctx, grad) if ctx.needs_input_grad[0] else None
+        gradB = _grad_B(ctx, grad) if ctx.needs_input_grad[1] else None
         return gradA, gradB
+
+
+def _grad_A(ctx, grad):
+    """grad_A[e] = <grad[i_e, :], B[j_e, :]> on A's pattern only (reference sparse_matmul.py:173-219)."""
+    saved = ctx.saved_tensors
+    A, B = saved[0], saved[1]
+    pat = ctx.pattern
+    if isinstance(pat, CsrPattern):
+        v = _ops.sddmm(pat, grad, B, None, pat.nnz_total)
+        return torch.sparse_csr_tensor(A.crow_indices(), A.col_indices(), v.view(A.values().shape), A.shape)
+    csr = cast(CooPattern, pat).csr
+    if not ctx.batched:
+        # per stored entry, in storage order (duplicates each get the full dot product)
+        v = _ops.sddmm(csr, grad, B, pat.out_index, csr.nnz_total)
+        return torch.sparse_coo_tensor(A._indices(), v, A.shape)
+    # batched COO: the gradient lives on the sorted unique pattern (reference :213-217)
+    v = _ops.sddmm(csr, grad, B, None, pat.nnz_unique)
+    return torch.sparse_coo_tensor(pat.grad_indices, v, A.shape)
+
+
+def _grad_B(ctx, grad):
+    """grad_B = A^T grad through the cached transposed structure (reference sparse_matmul.py:222-232)."""
+    saved = ctx.saved_tensors
+    A = saved[0]
+    pat = ctx.pattern
+    is_csr = isinstance(pat, CsrPattern)
+    csr = pat if is_csr else cast(CooPattern, pat).csr
+    if len(saved) > 2:
+        vals = saved[2]
+    elif is_csr:
+        vals = A.values().contiguous()
+    else:
+        vals = A._values().contiguous()
+    gradB = _ops.spmm(csr.transpose(), vals, grad, tag="spmm_gradB")
+    gradB = gradB if ctx.batched else gradB[0]
+    if ctx.B_strides is not None:
+        gradB = _ops.restride_like(gradB, ctx.B_shape, ctx.B_strides)
+    return gradB
