@@ -37,8 +37,15 @@ def _worker(rank, world, port, out):
         C = sparse_mm(A_full, B_full)
         C.backward(G)
         s, e = int(A.crow_indices()[lo]), int(A.crow_indices()[hi])
-        ok = (torch.equal(C_loc, C[lo:hi]) and torch.equal(A_loc.grad.values(), A_full.grad.values()[s:e])
+        # a row block may take a different kernel variant than the whole matrix (fewer rows): same sums,
+        # different lane tiling of K, so compare at fp32 rounding rather than bit for bit
+        ok = (torch.allclose(C_loc, C[lo:hi], rtol=1e-5, atol=1e-5)
+              and torch.allclose(A_loc.grad.values(), A_full.grad.values()[s:e], rtol=1e-5, atol=1e-5)
               and torch.allclose(B_rep.grad, B_full.grad, rtol=1e-5, atol=1e-5))
+        if not ok:
+            print("rank", rank, "max diffs", float((C_loc - C[lo:hi]).abs().max()),
+                  float((A_loc.grad.values() - A_full.grad.values()[s:e]).abs().max()),
+                  float((B_rep.grad - B_full.grad).abs().max()), flush=True)
         flags = [None] * world
         dist.all_gather_object(flags, bool(ok))
         if rank == 0:
