@@ -486,3 +486,58 @@ def test_public_sddmm_matches_solve_backward_idiom(layout):
     torch.testing.assert_close(sddmm(A, X, Y).double(), ref, rtol=1e-5, atol=1e-6)
     with pytest.raises(ValueError, match="Incompatible shapes"):
         sddmm(A, X, torch.rand(m, K + 1, device=DEV))
+
+
+# ------------------------------------------ persistent-tile kernels on oracle-sized inputs
+@pytest.fixture
+def force_tile_kernels(monkeypatch):
+    """Small problems normally take the row-split kernels; TSGU_TINY_ROWS=0 sends them through the
+    persistent bulk-copy-staged tile kernels so every (lanes-per-row x vectors-per-lane x dtype) variant
+    is checked against the oracle."""
+    import torchsparsegradutils_b200 as tsgu
+
+    monkeypatch.setenv("TSGU_TINY_ROWS", "0")
+    tsgu.clear_pattern_cache()
+    yield
+    tsgu.clear_pattern_cache()
+
+
+@pytest.mark.parametrize("K", [4, 8, 16, 24, 32, 64, 96, 128, 192, 256, 512])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.bfloat16])
+def test_tile_kernels_vs_oracle_all_K(K, dtype, force_tile_kernels):
+    if K % {torch.float32: 4, torch.float64: 2, torch.bfloat16: 8}[dtype]:
+        pytest.skip("K not vectorisable for this dtype: scalar row-split path, covered elsewhere")
+    n, m = 700, 450
+    A = rand_csr(n, m, 13, dtype=dtype, index_dtype=torch.int32, seed=K, ragged=True)
+    _check(A, torch.rand(m, K, device=DEV, dtype=dtype), torch.rand(n, K, device=DEV, dtype=dtype))
+
+
+@pytest.mark.parametrize("index_dtype", [torch.int32, torch.int64])
+def test_tile_kernels_batched_and_long_rows(index_dtype, force_tile_kernels):
+    A = rand_csr(300, 200, 9, batch=4, index_dtype=index_dtype, seed=21)
+    _check(A, torch.rand(4, 200, 128, device=DEV), torch.rand(4, 300, 128, device=DEV))
+    # a row longer than the staging capacity (tile falls back to direct loads) next to empty rows
+    n, m = 96, 9000
+    g = torch.Generator().manual_seed(5)
+    cnt = torch.zeros(n, dtype=torch.int64)
+    cnt[2], cnt[40], cnt[95] = 8200, 70, 3
+    crow = torch.zeros(n + 1, dtype=torch.int64)
+    crow[1:] = cnt.cumsum(0)
+    col = torch.cat([torch.randperm(m, generator=g)[:c].sort().values for c in cnt.tolist()])
+    A2 = torch.sparse_csr_tensor(crow.to(index_dtype).to(DEV), col.to(index_dtype).to(DEV),
+                                 torch.rand(col.numel(), generator=g).to(DEV), (n, m))
+    _check(A2, torch.rand(m, 64, device=DEV), torch.rand(n, 64, device=DEV))
+
+
+def test_tile_kernels_coo_value_permutation(force_tile_kernels):
+    """Uncoalesced COO: the tile SpMM stages the value permutation instead of the values, the SDDMM
+    scatters through out_index."""
+    n, m, nnz = 500, 300, 6000
+    g = torch.Generator().manual_seed(2)
+    flat = torch.randperm(n * m, generator=g)[:nnz]
+    idx = torch.stack([flat // m, flat % m])
+    idx = torch.cat([idx, idx[:, :300]], dim=1)  # duplicates, unsorted
+    A = torch.sparse_coo_tensor(idx.to(DEV), torch.rand(idx.shape[1], generator=g).to(DEV), (n, m))
+    _check(A, torch.rand(m, 32, device=DEV), torch.rand(n, 32, device=DEV))
+    Ab = torch.stack([A.coalesce(), A.coalesce()])
+    _check(Ab, torch.rand(2, m, 32, device=DEV), torch.rand(2, n, 32, device=DEV))

@@ -155,6 +155,14 @@ inline int64_t l2_bytes() {
   return cached;
 }
 
+// Problems with fewer rows than this cannot fill 148 SMs with row tiles and take the non-persistent
+// row-split kernels (one CTA per 256/LPR rows).  TSGU_TINY_ROWS overrides it (the parity tests set it to 0
+// so that small, oracle-sized inputs exercise every persistent-tile kernel variant).
+inline int64_t tiny_rows_threshold() {
+  const char* e = getenv("TSGU_TINY_ROWS");
+  return e ? atoll(e) : (int64_t)64 * 2 * kNumSMs;
+}
+
 // K-slicing for L2 residency.  When one item of the dense operand (rows x K) does not fit L2, every
 // gathered row is an HBM access and the kernel runs at HBM-gather speed (config 5: 6.5 TB/s).  Cutting K
 // into slices whose rows x Ks footprint fits L2 and running the slices as back-to-back launches turns

@@ -376,7 +376,7 @@ static int sddmm_dispatch(const SddmmParams<V, I>& p, int64_t m, int64_t nnz_tot
   if (fast_ok && algo == TSGU_ALGO_MERGE && p.batch == 1)
     return sddmm_merge_dispatch<V, I>(p.rowptr, p.colind, p.out_index, p.G, p.B, p.out, p.n, p.K, nnz_total, p.g_rs, p.b_rs,
                                       ws, ws_bytes, s);
-  const bool tiny = p.batch * p.n < 64 * 2 * kNumSMs;  // fewer rows than ~64 per resident CTA
+  const bool tiny = p.batch * p.n < tiny_rows_threshold();  // fewer rows than ~64 per resident CTA
   if (fast_ok && algo != TSGU_ALGO_ROWSPLIT && !tiny) {
     // L2 blocking (see pick_k_slice): partial dots of the K slices are accumulated into `out`
     const int64_t ks = pick_k_slice(m, p.K, (int)sizeof(V));

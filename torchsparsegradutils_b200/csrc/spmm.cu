@@ -354,7 +354,7 @@ static int spmm_dispatch(const SpmmParams<V, I>& p, int64_t m, int64_t nnz_total
     return spmm_merge_dispatch<V, I>(p.rowptr, p.colind, p.vals, p.perm, p.B, p.C, p.n, p.K, nnz_total, p.b_rs, p.ldc, ws,
                                      ws_bytes, s);
   // small problems cannot fill 148 SMs with 64-row tiles: one row per lane group, one CTA per 256/LPR rows
-  const bool tiny = p.batch * p.n < 64 * 2 * kNumSMs;  // fewer rows than ~64 per resident CTA
+  const bool tiny = p.batch * p.n < tiny_rows_threshold();  // fewer rows than ~64 per resident CTA
   if (fast_ok && algo != TSGU_ALGO_ROWSPLIT && !tiny) {
     // L2 blocking: run K in slices whose dense footprint stays L2-resident (see pick_k_slice)
     const int64_t ks = pick_k_slice(m, p.K, (int)sizeof(V));
