@@ -541,3 +541,32 @@ def test_tile_kernels_coo_value_permutation(force_tile_kernels):
     _check(A, torch.rand(m, 32, device=DEV), torch.rand(n, 32, device=DEV))
     Ab = torch.stack([A.coalesce(), A.coalesce()])
     _check(Ab, torch.rand(2, m, 32, device=DEV), torch.rand(2, n, 32, device=DEV))
+
+
+@pytest.mark.parametrize("layout", ["csr", "coo", "bcsr"])
+def test_graphed_step_matches_eager(layout):
+    """GraphedSparseMM replays forward+backward from one CUDA graph: same numbers as the eager op, also
+    after the values / dense operands change."""
+    from torchsparsegradutils_b200 import GraphedSparseMM
+
+    n, m, K = 400, 300, 64
+    if layout == "bcsr":
+        A = rand_csr(n, m, 7, batch=3, seed=1)
+        B, G = torch.rand(3, m, K, device=DEV), torch.rand(3, n, K, device=DEV)
+    else:
+        A = rand_csr(n, m, 7, seed=1, ragged=True)
+        if layout == "coo":
+            A = A.to_sparse_coo()
+        B, G = torch.rand(m, K, device=DEV), torch.rand(n, K, device=DEV)
+    step = GraphedSparseMM(A, B, G)
+    vals = A.values() if A.layout == torch.sparse_csr else A._values()
+    for trial in range(3):
+        v, Bt, Gt = vals * (trial + 1), B + trial, G - 0.5 * trial
+        C, gA, gB = step(v, Bt, Gt)
+        if A.layout == torch.sparse_csr:
+            At = torch.sparse_csr_tensor(A.crow_indices(), A.col_indices(), v, A.shape)
+        else:
+            At = torch.sparse_coo_tensor(A._indices(), v, A.shape, is_coalesced=A.is_coalesced())
+        C2, gA2, gB2 = _run(At, Bt, Gt)
+        gA2v = gA2.values() if A.layout == torch.sparse_csr else gA2._values()
+        assert torch.equal(C, C2) and torch.equal(gA.reshape(-1), gA2v.reshape(-1)) and torch.equal(gB, gB2)

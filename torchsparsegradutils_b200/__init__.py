@@ -8,8 +8,9 @@ index/layout helpers it depends on.  The arithmetic is hand-written sm_100a CUDA
 """
 from . import utils
 from ._pattern import clear_pattern_cache, set_pattern_cache_capacity
+from .graph import GraphedSparseMM
 from .sddmm import sddmm
 from .sparse_matmul import SparseMatMul, sparse_mm
 
-__all__ = ["sparse_mm", "SparseMatMul", "sddmm", "utils", "clear_pattern_cache", "set_pattern_cache_capacity"]
+__all__ = ["sparse_mm", "SparseMatMul", "sddmm", "GraphedSparseMM", "utils", "clear_pattern_cache", "set_pattern_cache_capacity"]
 __version__ = "0.1.0"
