@@ -1,14 +1,20 @@
-// spmm.cu -- row-split CSR SpMM for sm_100a:  C[t] = A[t] * B[t].
+// spmm.cu -- CSR SpMM for sm_100a:  C[t] = A[t] * B[t].
 //
 // Replaces torch.sparse.mm at reference sparse_matmul.py:155 (forward) and :229 (grad_B, with
-// the transposed structure from tsgu_csr_transpose + a value permutation).
+// the transposed structure from tsgu_csr_transpose).
 //
-// Mapping: a group of LPR lanes owns one row of A; the lanes tile the dense K dimension with
-// 128-bit loads (EPV elements each), VPL vectors per lane, so one B-row fetch is a single fully
-// coalesced request per vector slot.  The group loads LPR (col, val) pairs with one coalesced
-// request, then broadcasts them with shuffles and keeps U independent B-row loads in flight
-// before the FMA chain (HBM/L2-latency hiding by ILP; no tensor cores: 2 flop per 4-16 B).
-// Accumulation is in CSR order inside a row (deterministic, no atomics).
+// Three kernel families, chosen in spmm_dispatch():
+//   spmm_tile_kernel      persistent row tiles, sparse operand staged by the bulk-copy engine (tile.cuh):
+//                         the default whenever the dense operands are 128-bit addressable
+//   spmm_merge_kernel     merge-path, nnz-balanced (merge.cu): skewed row lengths, algo = MERGE
+//   spmm_rowsplit_kernel  one row per lane group, non-persistent: scalar / strided operands, K > 128
+//                         vectors, and problems too small to fill the GPU with tiles
+//
+// Common mapping: a group of LPR lanes owns one row of A; the lanes tile the dense K dimension with
+// 128-bit loads (EPV elements each), VPL vectors per lane, so one B-row fetch is one coalesced request
+// per vector slot.  (col, val) pairs are broadcast inside the group with shuffles and U independent
+// B-row loads are kept in flight before their FMA chain (latency hiding by ILP; no tensor cores: 2 flop
+// per 4-16 B).  Accumulation is in CSR order inside a row (deterministic, no atomics).
 #include <type_traits>
 
 #include "common.cuh"

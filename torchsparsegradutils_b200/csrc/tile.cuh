@@ -1,6 +1,6 @@
 // tile.cuh -- persistent row-tile pipeline shared by the SpMM and SDDMM fast paths (sm_100a).
 //
-// A CTA walks tiles of TILE_ROWS consecutive rows.  For every tile the three slices it needs from
+// A CTA walks tiles of consecutive rows (tile_rows, chosen per launch by pick_tile_rows).  For every tile the three slices it needs from
 // the sparse operand -- rowptr[r0 .. r1], colind[s .. e) and (SpMM) vals[s .. e) -- are contiguous in
 // global memory, so one elected thread streams them into shared memory with the bulk async-copy
 // engine (cp.async.bulk, SASS UBLKCP) completing on an mbarrier, one tile ahead of the warps that
