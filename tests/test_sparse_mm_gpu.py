@@ -570,3 +570,44 @@ def test_graphed_step_matches_eager(layout):
         C2, gA2, gB2 = _run(At, Bt, Gt)
         gA2v = gA2.values() if A.layout == torch.sparse_csr else gA2._values()
         assert torch.equal(C, C2) and torch.equal(gA.reshape(-1), gA2v.reshape(-1)) and torch.equal(gB, gB2)
+
+
+# ------------------------------------------------ split-row mode (long rows cut into virtual rows)
+@pytest.mark.parametrize("K", [16, 32, 64, 128, 160, 512, 10])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.bfloat16])
+def test_split_rows_vs_oracle(K, dtype, monkeypatch):
+    """Forced split-row SpMM / SDDMM / transposed SpMM on skewed rows vs the oracle (K = 10 is not
+    vectorisable and must fall back to the merge-path / row-split kernels)."""
+    import torchsparsegradutils_b200 as tsgu
+
+    monkeypatch.setenv("TSGU_B200_ALGO", "split")
+    monkeypatch.setenv("TSGU_TINY_ROWS", "0")
+    tsgu.clear_pattern_cache()
+    n, m = 1500, 12000
+    A = _skewed_csr(n, m, seed=K, dtype=dtype)
+    _check(A, torch.rand(m, K, device=DEV, dtype=dtype), torch.rand(n, K, device=DEV, dtype=dtype))
+    tsgu.clear_pattern_cache()
+
+
+@pytest.mark.parametrize("bound", ["16", "4096"])
+def test_split_rows_bounds_and_coo(bound, monkeypatch):
+    import torchsparsegradutils_b200 as tsgu
+    from torchsparsegradutils_b200 import _native as nat
+    from torchsparsegradutils_b200._pattern import csr_pattern
+
+    monkeypatch.setenv("TSGU_B200_ALGO", "split")
+    monkeypatch.setenv("TSGU_B200_SPLIT_BOUND", bound)
+    monkeypatch.setenv("TSGU_TINY_ROWS", "0")
+    tsgu.clear_pattern_cache()
+    Acsr = _skewed_csr(700, 5000, seed=3, index_dtype=torch.int64, hub_len=4000)
+    P = csr_pattern(Acsr)
+    assert P.algo == nat.ALGO_SPLIT and P.split is not None
+    lens = P.split.vrowptr[1:] - P.split.vrowptr[:-1]
+    assert int(lens.max()) <= int(bound) and int(lens.sum()) == Acsr._nnz()
+    _check(Acsr, torch.rand(5000, 32, device=DEV), torch.rand(700, 32, device=DEV))
+    crow, col, vals = Acsr.crow_indices(), Acsr.col_indices(), Acsr.values()
+    rows = torch.repeat_interleave(torch.arange(700, device=DEV), crow[1:] - crow[:-1])
+    sh = torch.randperm(col.numel(), device=DEV)
+    A = torch.sparse_coo_tensor(torch.stack([rows, col])[:, sh], vals[sh], (700, 5000))
+    _check(A, torch.rand(5000, 32, device=DEV), torch.rand(700, 32, device=DEV))
+    tsgu.clear_pattern_cache()

@@ -20,6 +20,7 @@ LIB_PATH = os.environ.get("TSGU_B200_LIB") or os.path.join(_HERE, "libtsgu_b200.
 F32, F64, BF16 = 0, 1, 2
 I32, I64 = 0, 1
 ALGO_AUTO, ALGO_ROWSPLIT, ALGO_MERGE = 0, 1, 2
+ALGO_SPLIT = 3  # host-side choice only: split long rows into virtual rows (tsgu_*_csr_split entry points)
 
 VAL_DTYPES = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16}
 IDX_DTYPES = {torch.int32: I32, torch.int64: I64}
@@ -34,6 +35,9 @@ _SIGNATURES = {
     "tsgu_spmm_workspace_bytes": (_Z, [_L, _L, _L, _L, _I, _I]),
     "tsgu_sddmm_csr": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _I, _I, _P, _Z, _P]),
     "tsgu_sddmm_workspace_bytes": (_Z, [_L, _L, _L, _I]),
+    "tsgu_spmm_csr_split": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _I, _I, _P]),
+    "tsgu_sddmm_csr_split": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _I, _I, _P]),
+    "tsgu_sum_row_pieces": (_I, [_P, _P, _P, _L, _L, _P, _L, _I, _I, _P]),
     "tsgu_sddmm_coo": (_I, [_P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _I, _P]),
     "tsgu_coo_sort": (_I, [_P, _I, _L, _L, _P, _I, _P, _P, _I, _P, _Z, _P]),
     "tsgu_coo_sort_workspace_bytes": (_Z, [_I, _L, _I]),

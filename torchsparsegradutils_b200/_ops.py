@@ -145,10 +145,25 @@ def _strides(x: torch.Tensor):
     return (bs if x.shape[0] > 1 else 0, rs if x.shape[1] > 1 else 0, cs if x.shape[2] > 1 else 1)
 
 
+def _split_ready(pat: CsrPattern, *dense: torch.Tensor) -> bool:
+    """Split-row mode needs the persistent-tile kernels: 128-bit addressable operands, K <= 128 vectors."""
+    if pat.split is None or pat.batch != 1:
+        return False
+    for x in dense:
+        if not _vector_ready(x) or x.shape[-1] // _VEC_ELEMS[x.dtype] > 128:
+            return False
+    return True
+
+
 def spmm(pat: CsrPattern, vals: torch.Tensor, dense: torch.Tensor, algo: Optional[int] = None,
          tag: str = "spmm") -> torch.Tensor:
     """out[t] = A[t] @ dense[t]; dense is (batch, m, K) (any strides); returns contiguous (batch, n, K)."""
     algo = pat.algo if algo is None else algo
+    if algo == nat.ALGO_SPLIT:
+        d3 = prepare_dense(_as3d(dense))
+        if _split_ready(pat, d3):
+            return _spmm_split(pat, vals, d3, tag)
+        algo = nat.ALGO_MERGE  # scalar / oversized K: the merge-path (or row-split) kernels take it
     dense = prepare_dense(_as3d(dense))
     K = dense.shape[-1]
     out = torch.empty((pat.batch, pat.n, K), dtype=dense.dtype, device=dense.device)
@@ -176,10 +191,51 @@ def spmm(pat: CsrPattern, vals: torch.Tensor, dense: torch.Tensor, algo: Optiona
     return out
 
 
+def _spmm_split(pat: CsrPattern, vals: torch.Tensor, dense: torch.Tensor, tag: str) -> torch.Tensor:
+    """SpMM over the virtual rows of a skewed pattern + ordered sum of the pieces of cut rows."""
+    sp = pat.split
+    dev = dense.device
+    K = dense.shape[-1]
+    out = torch.empty((1, pat.n, K), dtype=dense.dtype, device=dev)
+    acc_dtype = torch.float64 if dense.dtype == torch.float64 else torch.float32
+    partials = torch.empty((max(sp.num_pieces, 1), K), dtype=acc_dtype, device=dev)
+    L = nat.lib()
+    vdt = nat.val_enum(dense.dtype)
+    perm = pat.perm
+    if perm is not None and pat.nnz_total >= _PREGATHER_MIN_NNZ:
+        with _timer(tag + "_gather", dev):
+            vals = gather_values(vals.reshape(-1), perm)
+        perm = None
+    with _on(dev), _timer(tag, dev):
+        nat.check(L.tsgu_spmm_csr_split(nat.ptr(sp.vrowptr), nat.ptr(pat.colind), nat.ptr(vals), nat.ptr(perm),
+                                        nat.ptr(sp.row_map), dense.data_ptr(), out.data_ptr(), partials.data_ptr(),
+                                        sp.n_virtual, pat.m, K, pat.nnz_total, dense.stride(1) if dense.shape[1] > 1 else K, K,
+                                        vdt, pat.idx, nat.stream_ptr(dev)), "tsgu_spmm_csr_split")
+        if sp.num_pieces:
+            nat.check(L.tsgu_sum_row_pieces(partials.data_ptr(), nat.ptr(sp.cut_rows), nat.ptr(sp.cut_ptr),
+                                            sp.cut_rows.numel(), K, out.data_ptr(), K, vdt, pat.idx,
+                                            nat.stream_ptr(dev)), "tsgu_sum_row_pieces")
+    return out
+
+
 def sddmm(pat: CsrPattern, G: torch.Tensor, B: torch.Tensor, out_index: Optional[torch.Tensor], nnz_out: int,
           algo: Optional[int] = None) -> torch.Tensor:
     """values[dst(e)] = <G[t, r_e], B[t, c_e]> for every stored entry of the pattern."""
     algo = pat.algo if algo is None else algo
+    if algo == nat.ALGO_SPLIT:
+        G3, B3 = prepare_dense(_as3d(G)), prepare_dense(_as3d(B))
+        if nnz_out and _split_ready(pat, G3, B3):
+            sp = pat.split
+            out = torch.empty(nnz_out, dtype=B3.dtype, device=B3.device)
+            dev = B3.device
+            with _on(dev), _timer("sddmm", dev):
+                nat.check(nat.lib().tsgu_sddmm_csr_split(
+                    nat.ptr(sp.vrowptr), nat.ptr(pat.colind), nat.ptr(out_index), nat.ptr(sp.g_map), G3.data_ptr(),
+                    B3.data_ptr(), out.data_ptr(), sp.n_virtual, pat.m, B3.shape[-1], pat.nnz_total,
+                    G3.stride(1) if G3.shape[1] > 1 else G3.shape[-1], B3.stride(1) if B3.shape[1] > 1 else B3.shape[-1],
+                    nat.val_enum(B3.dtype), pat.idx, nat.stream_ptr(dev)), "tsgu_sddmm_csr_split")
+            return out
+        algo = nat.ALGO_MERGE
     G = prepare_dense(_as3d(G))
     B = prepare_dense(_as3d(B))
     out = torch.empty(nnz_out, dtype=B.dtype, device=B.device)

@@ -58,6 +58,7 @@ class CsrPattern:
     nnz_total: int
     idx: int  # nat.I32 / nat.I64
     algo: int = nat.ALGO_AUTO  # kernel family chosen once per pattern from its row-length skew
+    split: Optional["SplitRows"] = None  # virtual-row view of a skewed pattern (algo == ALGO_SPLIT)
     keep: tuple = ()  # tensors whose storage must outlive this pattern (cache-key owners)
     _transpose: Optional["CsrPattern"] = field(default=None, repr=False)
     _lock: threading.Lock = field(default_factory=threading.Lock, repr=False)
@@ -75,7 +76,45 @@ class CsrPattern:
         return self._transpose
 
 
-_ALGO_ENV = {"auto": None, "rowsplit": nat.ALGO_ROWSPLIT, "merge": nat.ALGO_MERGE}
+@dataclass
+class SplitRows:
+    """Long rows cut into consecutive pieces of at most `bound` entries over the same colind / vals arrays."""
+
+    vrowptr: torch.Tensor   # (n_virtual + 1,)
+    row_map: torch.Tensor   # SpMM: >= 0 the row of C, < 0 piece ~x of a cut row
+    g_map: torch.Tensor     # SDDMM: row of G each virtual row belongs to
+    cut_rows: torch.Tensor  # rows that were cut
+    cut_ptr: torch.Tensor   # (len(cut_rows) + 1,) piece ranges
+    n_virtual: int
+    num_pieces: int
+
+
+def build_split_rows(rowptr: torch.Tensor, n: int, nnz: int, bound: int) -> SplitRows:
+    """One-off per pattern (a handful of torch ops, two host syncs for the sizes)."""
+    dev, idt = rowptr.device, rowptr.dtype
+    rp = rowptr.reshape(-1).long()
+    lens = rp[1:] - rp[:-1]
+    nv = ((lens + (bound - 1)) // bound).clamp_(min=1)
+    first_v = torch.cumsum(nv, 0) - nv
+    n_virtual = int(nv.sum())
+    row_of_v = torch.repeat_interleave(torch.arange(n, device=dev), nv)
+    j = torch.arange(n_virtual, device=dev) - first_v[row_of_v]
+    vrowptr = torch.empty(n_virtual + 1, dtype=torch.int64, device=dev)
+    vrowptr[:-1] = rp[:-1][row_of_v] + j * bound
+    vrowptr[-1] = nnz
+    cut = nv > 1
+    is_piece = cut[row_of_v]
+    pidx = torch.cumsum(is_piece.long(), 0) - 1
+    row_map = torch.where(is_piece, -1 - pidx, row_of_v)
+    cut_rows = torch.nonzero(cut).flatten()
+    cut_ptr = torch.zeros(cut_rows.numel() + 1, dtype=torch.int64, device=dev)
+    cut_ptr[1:] = torch.cumsum(nv[cut], 0)
+    return SplitRows(vrowptr.to(idt), row_map.to(idt), row_of_v.to(idt), cut_rows.to(idt), cut_ptr.to(idt), n_virtual,
+                     int(is_piece.sum()))
+
+
+_ALGO_ENV = {"auto": None, "rowsplit": nat.ALGO_ROWSPLIT, "merge": nat.ALGO_MERGE, "split": nat.ALGO_SPLIT}
+_SKEWED_ALGO = nat.ALGO_MERGE  # what the skew heuristic picks (ALGO_MERGE or ALGO_SPLIT)
 
 
 def choose_algo(rowptr: torch.Tensor, batch: int, n: int, nnz_total: int) -> int:
@@ -86,14 +125,16 @@ def choose_algo(rowptr: torch.Tensor, batch: int, n: int, nnz_total: int) -> int
     pattern.  ``TSGU_B200_ALGO=auto|rowsplit|merge`` overrides the heuristic (benchmarking only).
     """
     forced = _ALGO_ENV.get(os.environ.get("TSGU_B200_ALGO", "auto").lower())
-    if forced is not None:
+    if forced is not None and forced != nat.ALGO_SPLIT:
         return forced
     if batch != 1 or nnz_total == 0 or n == 0:
         return nat.ALGO_AUTO
+    if forced is not None:
+        return forced
     flat = rowptr.reshape(-1)  # batch == 1: torch batched CSR keeps a leading dim of 1
     max_row = int((flat[1:] - flat[:-1]).max())
     mean = nnz_total / n
-    return nat.ALGO_MERGE if (max_row > 1024 and max_row > 32 * mean) else nat.ALGO_AUTO
+    return _SKEWED_ALGO if (max_row > 1024 and max_row > 32 * mean) else nat.ALGO_AUTO
 
 
 def _internal_idx(batch: int, rows: int, cols: int, nnz: int) -> int:
@@ -121,9 +162,19 @@ def _build_transpose(p: CsrPattern) -> CsrPattern:
         permT = p.perm.to(odt).index_select(0, permT.long()) if p.perm.dtype != odt else p.perm.index_select(0, permT.long())
     algo = choose_algo(rowptrT, p.batch, p.m, p.nnz_total)
     nnzT = p.nnz_total
-    if algo != nat.ALGO_MERGE and nnzT >= _PAD_MIN_NNZ:
+    if algo == nat.ALGO_AUTO and nnzT >= _PAD_MIN_NNZ:
         rowptrT, colindT, permT, nnzT = _pad_rows(rowptrT, colindT, permT, _ROW_PAD)
-    return CsrPattern(rowptrT, colindT, permT, p.batch, p.m, p.n, p.m, 0, nnzT, out_idx, algo=algo, keep=(p,))
+    return _with_split(CsrPattern(rowptrT, colindT, permT, p.batch, p.m, p.n, p.m, 0, nnzT, out_idx, algo=algo, keep=(p,)))
+
+
+def _split_bound() -> int:
+    return int(os.environ.get("TSGU_B200_SPLIT_BOUND", "128"))
+
+
+def _with_split(pat: CsrPattern) -> CsrPattern:
+    if pat.algo == nat.ALGO_SPLIT and pat.batch == 1:
+        pat.split = build_split_rows(pat.rowptr, pat.n, pat.nnz_total, _split_bound())
+    return pat
 
 
 _ROW_PAD = 4          # the row-split kernels consume a row in groups of >= 4 entries
@@ -187,8 +238,9 @@ def csr_pattern(A: torch.Tensor) -> CsrPattern:
     n, m = A.shape[-2], A.shape[-1]
     crow_c, col_c = crow.contiguous(), col.contiguous()
     nnz_item = col_c.shape[-1]
-    pat = CsrPattern(crow_c, col_c, None, batch, n, m, n + 1, nnz_item, batch * nnz_item,
-                     nat.idx_enum(crow.dtype), algo=choose_algo(crow_c, batch, n, batch * nnz_item), keep=(crow, col))
+    pat = _with_split(CsrPattern(crow_c, col_c, None, batch, n, m, n + 1, nnz_item, batch * nnz_item,
+                                 nat.idx_enum(crow.dtype), algo=choose_algo(crow_c, batch, n, batch * nnz_item),
+                                 keep=(crow, col)))
     _cache_put(key, pat)
     return pat
 
@@ -237,7 +289,8 @@ def _coo_to_flat_csr(indices: torch.Tensor, batch: int, n: int, m: int, perm: Op
         nat.check(nat.lib().tsgu_coo_to_csr(nat.ptr(indices), ndim, nnz, indices.stride(0), batch, n, nat.ptr(perm),
                                             nat.ptr(rowptr), nat.ptr(colind), idx, nat.stream_ptr(dev)),
                   "tsgu_coo_to_csr")
-    return CsrPattern(rowptr, colind, perm, batch, n, m, n, 0, nnz, idx, algo=choose_algo(rowptr, batch, n, nnz), keep=keep)
+    return _with_split(CsrPattern(rowptr, colind, perm, batch, n, m, n, 0, nnz, idx, algo=choose_algo(rowptr, batch, n, nnz),
+                                  keep=keep))
 
 
 def coo_pattern(A: torch.Tensor) -> CooPattern:

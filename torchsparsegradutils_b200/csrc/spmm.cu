@@ -34,6 +34,12 @@ struct SpmmParams {
   int64_t batch, n, K;
   int64_t rowptr_bstride, nnz_bstride;
   int64_t b_bs, b_rs, b_cs, c_bs, ldc;
+  // split-row mode (tile kernel, batch == 1): `rowptr` describes VIRTUAL rows (long rows cut into pieces of
+  // bounded length); row_map[v] >= 0 is the row of C a virtual row is (it was not cut), row_map[v] < 0 says
+  // "piece ~row_map[v] of a cut row": its partial sum goes to `partials` (accumulator type) and
+  // tsgu_sum_row_pieces adds the pieces up in order afterwards.
+  const I* row_map;
+  typename VT<V>::Acc* partials;
 };
 
 // EPV: elements per vector load (1 = scalar path that also honours b_cs != 1)
@@ -285,10 +291,22 @@ __global__ void __launch_bounds__(256, TSGU_TILE_MINB(VPL)) spmm_tile_kernel(con
           }
         }
       }
-      V* Crow = p.C + c.item * p.c_bs + (c.r0 + lr) * p.ldc;
+      int64_t dest = c.r0 + lr;
+      if (p.row_map) dest = (int64_t)p.row_map[dest];
+      if (dest >= 0) {
+        V* Crow = p.C + c.item * p.c_bs + dest * p.ldc;
 #pragma unroll
-      for (int w = 0; w < VPL; ++w)
-        if (EXACT || on[w]) store_vec<V, EPV>(Crow + (int64_t)(w * LPR + gl) * EPV, acc[w]);
+        for (int w = 0; w < VPL; ++w)
+          if (EXACT || on[w]) store_vec<V, EPV>(Crow + (int64_t)(w * LPR + gl) * EPV, acc[w]);
+      } else {  // a piece of a cut row: keep the partial in accumulator precision
+        Acc* Prow = p.partials + (~dest) * p.K;
+#pragma unroll
+        for (int w = 0; w < VPL; ++w)
+          if (EXACT || on[w]) {
+#pragma unroll
+            for (int i = 0; i < EPV; ++i) Prow[(int64_t)(w * LPR + gl) * EPV + i] = acc[w][i];
+          }
+      }
     }
     __syncthreads();  // everyone is done with this stage before it is refilled
   }
@@ -409,7 +427,33 @@ extern "C" int tsgu_spmm_csr(const void* rowptr, const void* colind, const void*
     p.batch = batch; p.n = n; p.K = K;
     p.rowptr_bstride = rowptr_bstride; p.nnz_bstride = nnz_bstride;
     p.b_bs = b_bs; p.b_rs = b_rs; p.b_cs = b_cs; p.c_bs = c_bs; p.ldc = ldc;
+    p.row_map = nullptr; p.partials = nullptr;
     return tsgu::spmm_dispatch<V, I>(p, m, nnz_total, algo, workspace, workspace_bytes, tsgu::as_stream(stream));
+  }));
+  return 0;
+}
+
+extern "C" int tsgu_spmm_csr_split(const void* vrowptr, const void* colind, const void* vals, const void* perm,
+                                   const void* row_map, const void* B, void* C, void* partials, int64_t n_virtual,
+                                   int64_t m, int64_t K, int64_t nnz_total, int64_t b_rs, int64_t ldc, int val_dtype,
+                                   int idx_dtype, void* stream) {
+  if (n_virtual < 0 || K < 0) return TSGU_ERR_SHAPE;
+  if (n_virtual == 0 || K == 0) return 0;
+  TSGU_DISPATCH_VAL(val_dtype, TSGU_DISPATCH_IDX(idx_dtype, {
+    constexpr int EPVF = 16 / sizeof(V);
+    tsgu::SpmmParams<V, I> p;
+    p.rowptr = (const I*)vrowptr; p.colind = (const I*)colind; p.vals = (const V*)vals;
+    p.perm = (const I*)perm; p.B = (const V*)B; p.C = (V*)C;
+    p.batch = 1; p.n = n_virtual; p.K = K;
+    p.rowptr_bstride = n_virtual; p.nnz_bstride = 0;
+    p.b_bs = 0; p.b_rs = b_rs; p.b_cs = 1; p.c_bs = 0; p.ldc = ldc;
+    p.row_map = (const I*)row_map; p.partials = (typename tsgu::VT<V>::Acc*)partials;
+    // split-row mode exists only for the persistent-tile kernels: the caller guarantees 128-bit operands
+    const bool ok = (K % EPVF) == 0 && K / EPVF <= 128 && (b_rs % EPVF) == 0 && (ldc % EPVF) == 0 && m < 0xffffffffLL &&
+                    b_rs * (int64_t)sizeof(V) < 0xffffffffLL && tsgu::aligned16(B) && tsgu::aligned16(C) &&
+                    tsgu::aligned16(vrowptr) && tsgu::aligned16(colind) && tsgu::aligned16(vals) && tsgu::aligned16(perm);
+    if (!ok) return TSGU_ERR_SHAPE;
+    return tsgu::spmm_tile_dispatch<V, I>(p, nnz_total, tsgu::as_stream(stream));
   }));
   return 0;
 }
