@@ -45,6 +45,10 @@ CONFIGS = {
               desc="R-MAT 2^22 rows ~64M nnz x dense 2^22x128 bf16 (BASELINE configs[3])"),
     "5": dict(kind="csr_uniform", n=262144, m=262144, per_row=8, K=512, dtype="f32", batch=None,
               desc="CSR 262144^2 8 nnz/row x dense 262144x512 fp32 (BASELINE configs[4])"),
+    # not a BASELINE config: the size of the reference's published suite-sparse case (Rothberg/cfd2,
+    # benchmarks/results/sparse_mm_suite_results.csv:6: fwd 722 us, fwd+bwd 73.1 ms on an RTX 4090), random pattern
+    "cfd2": dict(kind="csr_uniform", n=123440, m=123440, per_row=25, K=128, dtype="f32", batch=None,
+                 desc="cfd2-sized synthetic CSR 123440^2, 25 nnz/row (3 086 000 nnz) x dense 123440x128 fp32"),
     "5bf16": dict(kind="csr_uniform", n=262144, m=262144, per_row=8, K=512, dtype="bf16", batch=None,
                   desc="CSR 262144^2 8 nnz/row x dense 262144x512 bf16 (BASELINE configs[4])"),
 }
