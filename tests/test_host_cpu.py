@@ -147,3 +147,21 @@ def test_pattern_cache_api():
     tsgu.set_pattern_cache_capacity(4)
     tsgu.clear_pattern_cache()
     tsgu.set_pattern_cache_capacity(16)
+
+
+def test_batch_sparse_mv_rank_errors():
+    """Rank pairs outside the four supported ones raise the reference's message
+    (distributions/sparse_multivariate_normal.py:102) before any native call."""
+    import pytest
+    import torch
+
+    from torchsparsegradutils_b200 import batch_sparse_mv
+
+    A = torch.eye(3).to_sparse_csr()
+    with pytest.raises(ValueError, match="Invalid dimensions for bmat and bvec"):
+        batch_sparse_mv(A, torch.zeros(2, 3, 3))
+    with pytest.raises(ValueError, match="Invalid dimensions for bmat and bvec"):
+        batch_sparse_mv(A, torch.tensor(1.0))
+    calls = []
+    out = batch_sparse_mv(A, torch.ones(5, 3), op=lambda a, b: calls.append(tuple(b.shape)) or torch.zeros(3, 5))
+    assert calls == [(3, 5)] and out.shape == (5, 3)  # (k, n) vectors go in as a (n, k) view, come back as (k, n)

@@ -7,10 +7,11 @@ index/layout helpers it depends on.  The arithmetic is hand-written sm_100a CUDA
 ``include/tsgu_b200.h`` (``libtsgu_b200.so``); there is no CPU or PyTorch fallback.
 """
 from . import utils
+from .batch_mv import batch_sparse_mv
 from ._pattern import clear_pattern_cache, set_pattern_cache_capacity
 from .graph import GraphedSparseMM
 from .sddmm import sddmm
 from .sparse_matmul import SparseMatMul, sparse_mm
 
-__all__ = ["sparse_mm", "SparseMatMul", "sddmm", "GraphedSparseMM", "utils", "clear_pattern_cache", "set_pattern_cache_capacity"]
+__all__ = ["sparse_mm", "SparseMatMul", "sddmm", "batch_sparse_mv", "GraphedSparseMM", "utils", "clear_pattern_cache", "set_pattern_cache_capacity"]
 __version__ = "0.1.0"

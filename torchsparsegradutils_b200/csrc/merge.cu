@@ -9,6 +9,8 @@
 // the lane groups.  Rows cut by a group or tile boundary are completed in a fixed order (group
 // partials in shared memory, tile partials in a workspace + a small fix-up kernel): no float
 // atomics, bit-reproducible results.
+#include <climits>
+
 #include "common.cuh"
 #include "tile.cuh"
 
@@ -26,6 +28,9 @@
 #endif
 #ifndef TSGU_MERGE_LOADS
 #define TSGU_MERGE_LOADS 8   // 128-bit dense-row loads in flight per lane
+#endif
+#ifndef TSGU_MERGE_SDDMM_LOADS
+#define TSGU_MERGE_SDDMM_LOADS TSGU_MERGE_LOADS
 #endif
 
 namespace tsgu {
@@ -201,23 +206,29 @@ __global__ void __launch_bounds__(256, TSGU_MERGE_MINB) spmm_merge_kernel(const 
 #pragma unroll
       for (int i = 0; i < EPV; ++i) acc[w][i] = Acc(0);
 
-    int64_t row = gi0;
-    int64_t row_end = row < p.rows ? (int64_t)rp[(int)(row - ti0) + 1] : INT64_MAX;
-    const bool head_started_before = row < p.rows && (int64_t)rp[(int)(row - ti0)] < gj0;
+    // Tile-local 32-bit coordinates from here on (a tile holds at most MERGE_P entries and row ends):
+    // entries [gj0l, gj1l) and row ends [rowl, gi1l) belong to this group.  `row_end` is the local end of
+    // the current row, INT_MAX once the row does not finish inside this group's range.
+    const int gj0l = (int)(gj0 - tj0), gj1l = (int)(gj1 - tj0);
+    const int gi0l = (int)(gi0 - ti0), gi1l = (int)(gi1 - ti0);
+    int rowl = gi0l;
+    int row_end = rowl < gi1l ? (int)((int64_t)rp[rowl + 1] - tj0) : INT_MAX;
+    bool head = gi0 < p.rows && (int64_t)rp[gi0l] < gj0;  // the first row began before this group's range
     if (gl == 0) sm.head_row[group] = -1;
     if (tid == 0) p.carry_row[t * 2 + 0] = -1;  // overwritten after the barrier if this tile has a head partial
 
-    // finish `row`: interior rows go straight to C, a head row that began before this group's range
-    // is parked in shared memory for the ordered combine below
+    // finish the current row: interior rows go straight to C, a head row that began before this group's
+    // range is parked in shared memory for the ordered combine below
     auto flush = [&]() {
-      if (row == gi0 && head_started_before) {
+      if (head) {
 #pragma unroll
         for (int w = 0; w < VPL; ++w)
 #pragma unroll
           for (int i = 0; i < EPV; ++i) sm.head[group][(w * LPR + gl) * EPV + i] = acc[w][i];
-        if (gl == 0) sm.head_row[group] = row;
+        if (gl == 0) sm.head_row[group] = gi0;
+        head = false;
       } else {
-        V* Crow = p.C + row * p.ldc;
+        V* Crow = p.C + (ti0 + rowl) * p.ldc;
 #pragma unroll
         for (int w = 0; w < VPL; ++w)
           if (EXACT || on[w]) store_vec<V, EPV>(Crow + (int64_t)(w * LPR + gl) * EPV, acc[w]);
@@ -226,54 +237,80 @@ __global__ void __launch_bounds__(256, TSGU_MERGE_MINB) spmm_merge_kernel(const 
       for (int w = 0; w < VPL; ++w)
 #pragma unroll
         for (int i = 0; i < EPV; ++i) acc[w][i] = Acc(0);
-      ++row;
-      row_end = row < p.rows ? (int64_t)rp[(int)(row - ti0) + 1] : INT64_MAX;
+      ++rowl;
+      row_end = rowl < gi1l ? (int)((int64_t)rp[rowl + 1] - tj0) : INT_MAX;
+    };
+    auto accumulate = [&](const uint4 (&bu)[VPL], const Acc vj) {
+#pragma unroll
+      for (int w = 0; w < VPL; ++w) {
+        Acc x[EPV];
+        Raw<V, EPV> raw;
+        raw.bits = bu[w];
+        raw_unpack<V, EPV>(raw, x);
+#pragma unroll
+        for (int i = 0; i < EPV; ++i) acc[w][i] = fma(vj, x[i], acc[w][i]);
+      }
     };
 
-    for (int64_t base = gj0; base < gj1; base += LPR) {
-      const int64_t e = base + gl;
+    for (int basel = gj0l; basel < gj1l; basel += LPR) {
+      const int el = basel + gl;
       uint32_t cu = 0;
       Acc v = Acc(0);
-      if (e < gj1) {
-        cu = (uint32_t)scol[(int)(e - tj0)];
-        if constexpr (PERM) v = load_scalar<V>(p.vals + (int64_t)sprm[(int)(e - tj0)]);
-        else v = VT<V>::to_acc(sval[(int)(e - tj0)]);
+      if (el < gj1l) {
+        cu = (uint32_t)scol[el];
+        if constexpr (PERM) v = load_scalar<V>(p.vals + (int64_t)sprm[el]);
+        else v = VT<V>::to_acc(sval[el]);
       }
-      const int cnt = (int)min((int64_t)LPR, gj1 - base);
+      const int cnt = min(LPR, gj1l - basel);
       for (int j = 0; j < cnt; j += U) {
-        // U dense-row gathers in flight (they do not depend on the row structure) ...
-        uint4 b[U][VPL];
+        // all broadcasts of the batch first (one convergence check for the lot), then U dense-row gathers in
+        // flight (they do not depend on the row structure), then the segmented accumulation walks the rows
+        uint32_t cj[U];
+        Acc vj[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const uint32_t cj = shfl_idx(gmask, cu, j + u, LPR);
-          const char* brow = Bb + (uint64_t)cj * row_bytes;
-#pragma unroll
-          for (int w = 0; w < VPL; ++w) {
-            if (j + u < cnt && (EXACT || on[w])) b[u][w] = __ldg(reinterpret_cast<const uint4*>(brow + w * (LPR * 16)));
-            else b[u][w] = make_uint4(0, 0, 0, 0);
-          }
+          cj[u] = shfl_idx(gmask, cu, j + u, LPR);
+          vj[u] = shfl_idx(gmask, v, j + u, LPR);
         }
-        // ... then the segmented accumulation walks the rows
+        uint4 b[U][VPL];
+        if (j + U <= cnt) {  // full batch (group-uniform branch): nothing is predicated
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const Acc vj = shfl_idx(gmask, v, j + u, LPR);
-          if (j + u < cnt) {
-            const int64_t eu = base + j + u;
-            while (eu >= row_end && row < gi1) flush();  // also steps over empty rows
+          for (int u = 0; u < U; ++u) {
+            const char* brow = Bb + (uint64_t)cj[u] * row_bytes;
 #pragma unroll
             for (int w = 0; w < VPL; ++w) {
-              Acc x[EPV];
-              Raw<V, EPV> raw;
-              raw.bits = b[u][w];
-              raw_unpack<V, EPV>(raw, x);
+              if (EXACT || on[w]) b[u][w] = __ldg(reinterpret_cast<const uint4*>(brow + w * (LPR * 16)));
+              else b[u][w] = make_uint4(0, 0, 0, 0);
+            }
+          }
 #pragma unroll
-              for (int i = 0; i < EPV; ++i) acc[w][i] = fma(vj, x[i], acc[w][i]);
+          for (int u = 0; u < U; ++u) {
+            const int eu = basel + j + u;
+            while (eu >= row_end) flush();  // also steps over empty rows
+            accumulate(b[u], vj[u]);
+          }
+        } else {  // ragged end of this group's range
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const char* brow = Bb + (uint64_t)cj[u] * row_bytes;
+#pragma unroll
+            for (int w = 0; w < VPL; ++w) {
+              b[u][w] = make_uint4(0, 0, 0, 0);
+              if (j + u < cnt && (EXACT || on[w])) b[u][w] = __ldg(reinterpret_cast<const uint4*>(brow + w * (LPR * 16)));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (j + u < cnt) {
+              const int eu = basel + j + u;
+              while (eu >= row_end) flush();
+              accumulate(b[u], vj[u]);
             }
           }
         }
       }
     }
-    while (row < gi1) flush();  // rows whose end lies in this group's range but have no entry left
+    while (rowl < gi1l) flush();  // rows whose end lies in this group's range but have no entry left
     // what is left belongs to row gi1, which finishes in a later group / tile
 #pragma unroll
     for (int w = 0; w < VPL; ++w)
@@ -568,25 +605,32 @@ __global__ void __launch_bounds__(256, TSGU_MERGE_SDDMM_MINB) sddmm_merge_kernel
     const I* scol = st.col + (int)(tj0 & (AI - 1));
     const int nnz_t = (int)(tj1 - tj0);
 
-    // entries are split evenly over the groups (multiples of NB so every batch is full but the last)
+    // entries are split evenly over the groups (multiples of NB so every batch is full but the last);
+    // tile-local 32-bit coordinates: this group's entries are [gj0l, gj1l)
     int per = (nnz_t + GROUPS - 1) / GROUPS;
     per = (per + NB - 1) / NB * NB;
-    int64_t gj0 = tj0 + (int64_t)group * per, gj1 = gj0 + per;
-    if (gj0 > tj1) gj0 = tj1;
-    if (gj1 > tj1) gj1 = tj1;
+    int gj0l = group * per, gj1l = gj0l + per;
+    if (gj0l > nnz_t) gj0l = nnz_t;
+    if (gj1l > nnz_t) gj1l = nnz_t;
 
-    if (gj0 < gj1) {
+    if (gj0l < gj1l) {
       // row of the first entry: last row r in the slice with rowptr[r] <= gj0
+      const int64_t gj0 = tj0 + gj0l;
       int lo = 0, hi = (int)(ti1 - ti0) + 1;  // rp[lo] <= gj0 < rp[hi] (rp[rows_t + 1] > tj1 - 1 >= gj0)
       while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
         if ((int64_t)rp[mid] <= gj0) lo = mid; else hi = mid;
       }
-      int64_t row = ti0 + lo;
-      int64_t row_end = (int64_t)rp[lo + 1];
+      int rowl = lo;
+      // local end of the current row, clamped: a row that runs past the tile ends "never" for this tile
+      auto local_end = [&](int r) {
+        const int64_t d = (int64_t)rp[r + 1] - tj0;
+        return d > (int64_t)nnz_t ? INT_MAX : (int)d;
+      };
+      int row_end = local_end(rowl);
       Acc g[VPL][EPV];
       auto load_g = [&]() {
-        const V* Grow = p.G + row * p.g_rs;
+        const V* Grow = p.G + (ti0 + rowl) * p.g_rs;
 #pragma unroll
         for (int w = 0; w < VPL; ++w) {
           Raw<V, EPV> raw = (EXACT || on[w]) ? raw_ldg<V, EPV>(Grow + (int64_t)(w * LPR + gl) * EPV) : raw_zero<V, EPV>();
@@ -594,18 +638,36 @@ __global__ void __launch_bounds__(256, TSGU_MERGE_SDDMM_MINB) sddmm_merge_kernel
         }
       };
       load_g();
+      auto next_row = [&](int eu) {  // skip empties, fetch that row of G
+        do {
+          ++rowl;
+          row_end = local_end(rowl);
+        } while (eu >= row_end);
+        load_g();
+      };
+      auto dot = [&](const uint4 (&bu)[VPL], Acc& out) {
+#pragma unroll
+        for (int w = 0; w < VPL; ++w) {
+          Acc x[EPV];
+          Raw<V, EPV> raw;
+          raw.bits = bu[w];
+          raw_unpack<V, EPV>(raw, x);
+#pragma unroll
+          for (int i = 0; i < EPV; ++i) out = fma(g[w][i], x[i], out);
+        }
+      };
 
-      for (int64_t base = gj0; base < gj1; base += NB) {
-        const int64_t e = base + gl;
+      for (int basel = gj0l; basel < gj1l; basel += NB) {
+        const int el = basel + gl;
         uint32_t cu = 0;
-        if (gl < NB && e < gj1) cu = (uint32_t)scol[(int)(e - tj0)];
-        const int cnt = (int)min((int64_t)NB, gj1 - base);
+        if (gl < NB && el < gj1l) cu = (uint32_t)scol[el];
+        const int cnt = min(NB, gj1l - basel);
         Acc part[NB];
 #pragma unroll
         for (int j = 0; j < NB; ++j) part[j] = Acc(0);
+        if (cnt == NB) {  // full batch (group-uniform branch): nothing is predicated
 #pragma unroll
-        for (int j0 = 0; j0 < NB; j0 += U) {
-          if (j0 < cnt) {
+          for (int j0 = 0; j0 < NB; j0 += U) {
             uint4 b[U][VPL];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -613,29 +675,38 @@ __global__ void __launch_bounds__(256, TSGU_MERGE_SDDMM_MINB) sddmm_merge_kernel
               const char* brow = Bb + (uint64_t)cj * row_bytes;
 #pragma unroll
               for (int w = 0; w < VPL; ++w) {
-                if (j0 + u < cnt && (EXACT || on[w])) b[u][w] = __ldg(reinterpret_cast<const uint4*>(brow + w * (LPR * 16)));
+                if (EXACT || on[w]) b[u][w] = __ldg(reinterpret_cast<const uint4*>(brow + w * (LPR * 16)));
                 else b[u][w] = make_uint4(0, 0, 0, 0);
               }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-              if (j0 + u < cnt) {
-                const int64_t eu = base + j0 + u;
-                if (eu >= row_end) {  // next row(s): skip empties, fetch that row of G
-                  do {
-                    ++row;
-                    row_end = (int64_t)rp[(int)(row - ti0) + 1];
-                  } while (eu >= row_end);
-                  load_g();
-                }
+              const int eu = basel + j0 + u;
+              if (eu >= row_end) next_row(eu);
+              dot(b[u], part[j0 + u]);
+            }
+          }
+        } else {  // ragged end of this group's range
+#pragma unroll
+          for (int j0 = 0; j0 < NB; j0 += U) {
+            if (j0 < cnt) {
+              uint4 b[U][VPL];
+#pragma unroll
+              for (int u = 0; u < U; ++u) {
+                const uint32_t cj = shfl_idx(gmask, cu, j0 + u, LPR);
+                const char* brow = Bb + (uint64_t)cj * row_bytes;
 #pragma unroll
                 for (int w = 0; w < VPL; ++w) {
-                  Acc x[EPV];
-                  Raw<V, EPV> raw;
-                  raw.bits = b[u][w];
-                  raw_unpack<V, EPV>(raw, x);
+                  b[u][w] = make_uint4(0, 0, 0, 0);
+                  if (j0 + u < cnt && (EXACT || on[w])) b[u][w] = __ldg(reinterpret_cast<const uint4*>(brow + w * (LPR * 16)));
+                }
+              }
 #pragma unroll
-                  for (int i = 0; i < EPV; ++i) part[j0 + u] = fma(g[w][i], x[i], part[j0 + u]);
+              for (int u = 0; u < U; ++u) {
+                if (j0 + u < cnt) {
+                  const int eu = basel + j0 + u;
+                  if (eu >= row_end) next_row(eu);
+                  dot(b[u], part[j0 + u]);
                 }
               }
             }
@@ -644,7 +715,7 @@ __global__ void __launch_bounds__(256, TSGU_MERGE_SDDMM_MINB) sddmm_merge_kernel
         butterfly_reduce_m<Acc, LPR, NB>(part, gmask, gl);
         const int slot = gl / LPE;
         if ((gl % LPE) == 0 && slot < cnt) {
-          const int64_t eo = base + slot;
+          const int64_t eo = tj0 + basel + slot;
           int64_t dst = eo;
           if (p.out_index) dst = (int64_t)__ldg(p.out_index + eo);
           if (dst >= 0) p.out[dst] = VT<V>::from_acc(part[0]);
@@ -659,7 +730,7 @@ template <typename V, typename I, int LPR, int VPL>
 static int launch_sddmm_merge(const MergeSddmmParams<V, I>& p0, void* ws, size_t ws_bytes, cudaStream_t s) {
   constexpr int EPV = 16 / sizeof(V);
   constexpr int NB = LPR < 16 ? LPR : 16;
-  constexpr int U0 = TSGU_MERGE_LOADS / VPL;
+  constexpr int U0 = TSGU_MERGE_SDDMM_LOADS / VPL;
   constexpr int U = U0 < NB ? U0 : NB;
   MergeSddmmParams<V, I> p = p0;
   const int64_t num_tiles = (p.rows + p.nnz + MERGE_P - 1) / MERGE_P;

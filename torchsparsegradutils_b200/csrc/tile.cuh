@@ -23,6 +23,9 @@
 #ifndef TSGU_LPR_CAP
 #define TSGU_LPR_CAP 8     // widest lane group the tile kernels use (8 / 16 / 32)
 #endif
+#ifndef TSGU_TILE_STAGE_BYTES
+#define TSGU_TILE_STAGE_BYTES 32768  // colind + vals bytes staged per tile and stage
+#endif
 #ifndef TSGU_TILE_ROWS
 #define TSGU_TILE_ROWS 128  // most rows a tile may hold; the launcher picks tile_rows <= this from nnz/row
 #endif
@@ -64,7 +67,7 @@ template <typename V, typename I, int VALS>
 struct TileCfg {
   static constexpr int TILE_ROWS = TSGU_TILE_ROWS;
   // entries of colind / vals staged per tile: 32 KB per stage (4096 for fp32 + int32)
-  static constexpr int CAP = (32768 / (int)(sizeof(I) + (VALS == 1 ? sizeof(V) : VALS == 2 ? sizeof(I) : 0))) & ~15;
+  static constexpr int CAP = (TSGU_TILE_STAGE_BYTES / (int)(sizeof(I) + (VALS == 1 ? sizeof(V) : VALS == 2 ? sizeof(I) : 0))) & ~15;
   static constexpr int ALN_I = 16 / (int)sizeof(I);
   static constexpr int ALN_V = 16 / (int)sizeof(V);
   static constexpr int STAGES = 2;
