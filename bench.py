@@ -6,8 +6,9 @@
 One step = one forward + backward of ``sparse_mm(A, B)`` (C = A B; grad_A by SDDMM; grad_B = A^T G)
 over one batch of synthetic input.  Default workload = BASELINE.json configs[1] ("config 2"): batched
 CSR, batch 8, 65536 x 65536, 16 nnz/row, dense 65536 x 128, fp32 / int32.  With N > 1 (launched by
-torchrun, one rank per GPU) the 8 batch items are sharded across the ranks -- independent items, no
-data-path collective (strong scaling: total work fixed).
+torchrun, one rank per GPU) batch items are independent units with no data-path collective: by default
+every rank runs a full batch of 8 of its own (weak scaling, global batch 8 N); ``--scaling strong`` splits
+the 8 items of BASELINE's literal config over the ranks instead.
 
 Prints ONE JSON line (rank 0).  `value` = nnz/s with inputs resident in HBM; `e2e` = the same metric
 through the public API from pinned HOST buffers (H2D of A, B, G and D2H of C, grad_A, grad_B inside

@@ -3,5 +3,5 @@
 # (built with scripts described in DESIGN.md section 3.2; TSGU_B200_LIB selects the library).
 for lib in ${LIBS:-$(ls variants_tmp/lib_*.so)}; do
   echo "== $lib"
-  TSGU_B200_LIB=$PWD/$lib CONFIGS=${CONFIGS:-4} STEPS=${STEPS:-10} bash scripts/bench_all_configs.sh | tail -1
+  TSGU_B200_LIB=$PWD/$lib CONFIGS=${CONFIGS:-4} STEPS=${STEPS:-10} bash scripts/bench_all_configs.sh | grep -v "^=="
 done

@@ -18,19 +18,19 @@
 #define TSGU_MERGE_P 2048
 #endif
 #ifndef TSGU_MERGE_MINB
-#define TSGU_MERGE_MINB 3   // resident CTAs per SM the register allocation aims for (swept on config 4)
+#define TSGU_MERGE_MINB 2   // resident CTAs per SM the register allocation aims for (swept on config 4: 2 CTAs x 16 loads beat 3 x 8)
 #endif
 #ifndef TSGU_MERGE_SDDMM_MINB
-#define TSGU_MERGE_SDDMM_MINB 4
+#define TSGU_MERGE_SDDMM_MINB 3
 #endif
 #ifndef TSGU_MERGE_NARROW
 #define TSGU_MERGE_NARROW 1  // 8-lane groups with 2-4 vectors per lane, as the tile kernels (config 4: 9.7 -> 9.2 ms)
 #endif
 #ifndef TSGU_MERGE_LOADS
-#define TSGU_MERGE_LOADS 8   // 128-bit dense-row loads in flight per lane
+#define TSGU_MERGE_LOADS 16  // 128-bit dense-row loads in flight per lane (SpMM)
 #endif
 #ifndef TSGU_MERGE_SDDMM_LOADS
-#define TSGU_MERGE_SDDMM_LOADS TSGU_MERGE_LOADS
+#define TSGU_MERGE_SDDMM_LOADS 8  // ... and in the SDDMM, which wants more warps instead (row changes stall on a G-row fetch)
 #endif
 
 namespace tsgu {
