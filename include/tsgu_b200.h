@@ -52,6 +52,10 @@ enum { TSGU_F32 = 0, TSGU_F64 = 1, TSGU_BF16 = 2 };
 enum { TSGU_I32 = 0, TSGU_I64 = 1 };
 /* kernel selection (AUTO: nnz-imbalance heuristic done by the caller) */
 enum { TSGU_ALGO_AUTO = 0, TSGU_ALGO_ROWSPLIT = 1, TSGU_ALGO_MERGE = 2 };
+/* hint OR-ed into `algo` of tsgu_spmm_csr: the rows of this pattern have (near-)uniform length, so when one item
+ * of the dense operand exceeds L2 the K dimension may be processed in L2-resident slices (same results: the
+ * slices are independent columns of C).  Ignored by every other entry point. */
+#define TSGU_ALGO_FLAG_KSLICE 0x100
 /* argument errors */
 enum {
   TSGU_ERR_DTYPE = -1,      /* unknown value / index dtype enum              */

@@ -215,3 +215,21 @@ def test_config3_stencil_pattern_and_column_major_B():
     C2.backward(G)
     assert torch.equal(C1, C2) and torch.equal(B1.grad, B2.grad)
     assert B1.grad.stride() == B1.stride() and C1.is_contiguous()
+
+
+def test_k_sliced_forward_matches_unsliced():
+    """Uniform rows + a dense operand larger than L2 (128 MiB): the forward SpMM runs K in L2-resident slices
+    (TSGU_ALGO_FLAG_KSLICE).  Slices are independent columns of C, so the result must equal the row-split
+    kernel's (same CSR accumulation order) -- and the ragged transposed pattern must not ask for slicing."""
+    from torchsparsegradutils_b200 import _native as nat
+    from torchsparsegradutils_b200 import _ops
+    from torchsparsegradutils_b200._pattern import csr_pattern
+
+    n = m = 65536
+    A = W.uniform_rows_csr(None, n, m, 8, torch.float32, torch.int32, DEV, seed=11)
+    B, _ = W.dense_operands((n, m), 512, torch.float32, DEV, seed=12)
+    pat = csr_pattern(A)
+    assert pat.uniform_rows and not pat.transpose().uniform_rows
+    C_sliced = _ops.spmm(pat, A.values(), B)  # default path: flag set by the launcher
+    C_plain = _ops.spmm(pat, A.values(), B, algo=nat.ALGO_ROWSPLIT)
+    torch.testing.assert_close(C_sliced, C_plain, rtol=1e-6, atol=1e-6)

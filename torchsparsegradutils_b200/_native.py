@@ -20,6 +20,7 @@ LIB_PATH = os.environ.get("TSGU_B200_LIB") or os.path.join(_HERE, "libtsgu_b200.
 F32, F64, BF16 = 0, 1, 2
 I32, I64 = 0, 1
 ALGO_AUTO, ALGO_ROWSPLIT, ALGO_MERGE = 0, 1, 2
+ALGO_FLAG_KSLICE = 0x100  # OR-ed into algo for tsgu_spmm_csr: uniform rows, K may be cut into L2-resident slices
 ALGO_SPLIT = 3  # host-side choice only: split long rows into virtual rows (tsgu_*_csr_split entry points)
 
 VAL_DTYPES = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16}

@@ -155,6 +155,16 @@ def _split_ready(pat: CsrPattern, *dense: torch.Tensor) -> bool:
     return True
 
 
+_L2_BYTES = {}
+
+
+def _l2_bytes(dev: torch.device) -> int:
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _L2_BYTES:
+        _L2_BYTES[key] = int(torch.cuda.get_device_properties(key).L2_cache_size)
+    return _L2_BYTES[key]
+
+
 def spmm(pat: CsrPattern, vals: torch.Tensor, dense: torch.Tensor, algo: Optional[int] = None,
          tag: str = "spmm") -> torch.Tensor:
     """out[t] = A[t] @ dense[t]; dense is (batch, m, K) (any strides); returns contiguous (batch, n, K)."""
@@ -179,6 +189,8 @@ def spmm(pat: CsrPattern, vals: torch.Tensor, dense: torch.Tensor, algo: Optiona
         with _timer(tag + "_gather", dev):
             vals = gather_values(vals.reshape(-1), perm)
         perm = None
+    if (algo == nat.ALGO_AUTO and pat.m * K * dense.element_size() > (_l2_bytes(dev) * 3) // 5 and pat.uniform_rows):
+        algo |= nat.ALGO_FLAG_KSLICE  # dense operand exceeds L2 and the rows are uniform: L2-resident K slices
     with _on(dev), _timer(tag, dev):
         ws_bytes = L.tsgu_spmm_workspace_bytes(pat.batch, pat.n, K, pat.nnz_total, vdt, algo) if algo == nat.ALGO_MERGE else 0
         ws = nat.workspace(ws_bytes, dev) if ws_bytes else None

@@ -61,11 +61,27 @@ class CsrPattern:
     split: Optional["SplitRows"] = None  # virtual-row view of a skewed pattern (algo == ALGO_SPLIT)
     keep: tuple = ()  # tensors whose storage must outlive this pattern (cache-key owners)
     _transpose: Optional["CsrPattern"] = field(default=None, repr=False)
+    _uniform: Optional[bool] = field(default=None, repr=False)
     _lock: threading.Lock = field(default_factory=threading.Lock, repr=False)
 
     @property
     def device(self) -> torch.device:
         return self.rowptr.device
+
+    @property
+    def uniform_rows(self) -> bool:
+        """True when no row is much longer than the mean (longest <= 1.25 x mean + 1).  Evaluated lazily, once per
+        pattern (one host sync), and only asked for when the dense operand exceeds L2: it gates the K-sliced
+        forward SpMM (``TSGU_ALGO_FLAG_KSLICE``), which loses on ragged rows."""
+        if self._uniform is None:
+            rows = self.batch * self.n
+            if rows == 0 or self.nnz_total == 0:
+                self._uniform = False
+            else:
+                rp = self.rowptr.reshape(self.batch, -1) if self.rowptr_bstride == self.n + 1 else self.rowptr.reshape(1, -1)
+                longest = int((rp[:, 1:] - rp[:, :-1]).max())
+                self._uniform = longest <= 1.25 * (self.nnz_total / rows) + 1
+        return self._uniform
 
     def transpose(self) -> "CsrPattern":
         """CSR of the transposes (flat over batch*m rows), built once by tsgu_csr_transpose."""

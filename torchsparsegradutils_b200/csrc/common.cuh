@@ -164,21 +164,27 @@ inline int64_t tiny_rows_threshold() {
 }
 
 // K-slicing for L2 residency.  When one item of the dense operand (rows x K) does not fit L2, every
-// gathered row is an HBM access and the kernel runs at HBM-gather speed (config 5: 6.5 TB/s).  Cutting K
+// gathered row is an HBM access and the kernel runs at HBM-gather speed (config 5: 6.6 TB/s).  Cutting K
 // into slices whose rows x Ks footprint fits L2 and running the slices as back-to-back launches turns
 // the re-reads of a row (once per nonzero of that column) into L2 hits; the sparse structure is re-read
 // once per slice, which is small next to the dense traffic.  Returns Ks (== K: do not slice).
-inline int64_t pick_k_slice(int64_t rows, int64_t K, int elem_bytes) {
+// Measured on config 5 (fp32, K = 512 -> 8 slices of 64): forward SpMM over uniform rows 0.646 -> 0.496 ms,
+// but the SDDMM (0.62 -> 0.68 ms) and the SpMM over the ragged transposed rows (0.64 -> 0.87 ms: narrower lane
+// groups put 4 rows of different lengths in one warp) lose.  So slicing is on only where the caller says the
+// rows are uniform (`allow`: TSGU_ALGO_FLAG_KSLICE, forward SpMM); env TSGU_L2_SLICE_FRAC=<share of L2 per
+// slice> forces it everywhere (experiments), <= 0 disables it.
+inline int64_t pick_k_slice(int64_t rows, int64_t K, int elem_bytes, bool allow = false) {
   const int64_t l2 = l2_bytes();
   const int64_t epv = 16 / elem_bytes;
-  static double frac = 0.0;  // share of L2 one slice may occupy (env TSGU_L2_SLICE_FRAC; <= 0 disables slicing)
-  if (frac == 0.0) {
+  static double env_frac = -2.0;  // -2: not read yet; -1: unset
+  if (env_frac == -2.0) {
     const char* e = getenv("TSGU_L2_SLICE_FRAC");
-    frac = e ? atof(e) : 0.0;  // off by default: helps regular rows (config 5 fwd 0.65 -> 0.49 ms at 0.55) but the
-                               // shorter per-slice groups make ragged (transposed) rows 1.6x slower; see DESIGN.md
-    if (frac <= 0.0) frac = -1.0;
+    env_frac = e ? atof(e) : -1.0;
   }
-  if (frac < 0.0 || rows * K * elem_bytes <= (l2 * 3) / 5) return K;
+  double frac;
+  if (env_frac != -1.0) frac = env_frac;
+  else frac = allow ? 0.55 : 0.0;
+  if (frac <= 0.0 || rows * K * elem_bytes <= (l2 * 3) / 5) return K;
   for (int64_t parts = 2; parts <= 64; parts *= 2) {
     if (K % parts) break;
     const int64_t ks = K / parts;

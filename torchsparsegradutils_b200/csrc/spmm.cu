@@ -367,8 +367,10 @@ static int spmm_tile_dispatch(const SpmmParams<V, I>& p, int64_t nnz_total, cuda
 }
 
 template <typename V, typename I>
-static int spmm_dispatch(const SpmmParams<V, I>& p, int64_t m, int64_t nnz_total, int algo, void* ws, size_t ws_bytes,
+static int spmm_dispatch(const SpmmParams<V, I>& p, int64_t m, int64_t nnz_total, int algo_flags, void* ws, size_t ws_bytes,
                          cudaStream_t s) {
+  const int algo = algo_flags & ~TSGU_ALGO_FLAG_KSLICE;
+  const bool uniform_rows = (algo_flags & TSGU_ALGO_FLAG_KSLICE) != 0;
   constexpr int EPVF = 16 / sizeof(V);
   const bool vec_ok = p.b_cs == 1 && (p.K % EPVF) == 0 && (p.b_rs % EPVF) == 0 && (p.b_bs % EPVF) == 0 &&
                       (p.ldc % EPVF) == 0 && (p.c_bs % EPVF) == 0 && aligned16(p.B) && aligned16(p.C);
@@ -381,7 +383,7 @@ static int spmm_dispatch(const SpmmParams<V, I>& p, int64_t m, int64_t nnz_total
   const bool tiny = p.batch * p.n < tiny_rows_threshold();  // fewer rows than ~64 per resident CTA
   if (fast_ok && algo != TSGU_ALGO_ROWSPLIT && !tiny) {
     // L2 blocking: run K in slices whose dense footprint stays L2-resident (see pick_k_slice)
-    const int64_t ks = pick_k_slice(m, p.K, (int)sizeof(V));
+    const int64_t ks = pick_k_slice(m, p.K, (int)sizeof(V), uniform_rows);
     if (ks < p.K) {
       for (int64_t k0 = 0; k0 < p.K; k0 += ks) {
         SpmmParams<V, I> q = p;
@@ -418,7 +420,10 @@ extern "C" int tsgu_spmm_csr(const void* rowptr, const void* colind, const void*
                              int val_dtype, int idx_dtype, int algo, void* workspace,
                              size_t workspace_bytes, void* stream) {
   if (batch < 0 || n < 0 || K < 0) return TSGU_ERR_SHAPE;
-  if (algo != TSGU_ALGO_AUTO && algo != TSGU_ALGO_ROWSPLIT && algo != TSGU_ALGO_MERGE) return TSGU_ERR_ALGO;
+  {
+    const int family = algo & ~TSGU_ALGO_FLAG_KSLICE;
+    if (family != TSGU_ALGO_AUTO && family != TSGU_ALGO_ROWSPLIT && family != TSGU_ALGO_MERGE) return TSGU_ERR_ALGO;
+  }
   if (batch == 0 || n == 0 || K == 0) return 0;
   TSGU_DISPATCH_VAL(val_dtype, TSGU_DISPATCH_IDX(idx_dtype, {
     tsgu::SpmmParams<V, I> p;
@@ -460,6 +465,6 @@ extern "C" int tsgu_spmm_csr_split(const void* vrowptr, const void* colind, cons
 
 extern "C" size_t tsgu_spmm_workspace_bytes(int64_t batch, int64_t n, int64_t K, int64_t nnz_total,
                                             int val_dtype, int algo) {
-  if (algo == TSGU_ALGO_MERGE && batch == 1) return tsgu::spmm_merge_workspace_bytes(n, K, nnz_total, val_dtype);
+  if ((algo & ~TSGU_ALGO_FLAG_KSLICE) == TSGU_ALGO_MERGE && batch == 1) return tsgu::spmm_merge_workspace_bytes(n, K, nnz_total, val_dtype);
   return 0;
 }
