@@ -215,7 +215,8 @@ def main():
         base = cpu_reference_run(cfg, steps=max(1, min(args.steps, 3)), warmup=1)
         line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": base["steps"], "warmup": 1, "ms_per_step": base["ms_per_step"], "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_out,
+                "scaling": (args.scaling if cfg.get("batch") else "strong"), "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config_out,
                 "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}

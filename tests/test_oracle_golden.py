@@ -97,3 +97,28 @@ def test_reference_port_matches_golden(name):
     np.testing.assert_allclose(C.numpy(), g("C"), **t)
     np.testing.assert_allclose(gB.numpy(), g("gradB"), **t)
     np.testing.assert_allclose(gA.numpy().reshape(g("gradA_values").shape), g("gradA_values"), **t)
+
+
+def test_oracle_sddmm_reproduces_reference_solve_gradients():
+    """The oracle's SDDMM, negated, equals A.grad of the reference's triangular / generic solves
+    (tests/golden/solve_grad_cases.npz; sparse_solve.py:216-235, :487-504) -- pins SURVEY 8(f) rank 1."""
+    import os
+
+    import numpy as np
+
+    from oracle import oracle as orc
+
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "solve_grad_cases.npz"))
+    for name in [str(c) for c in G["__cases__"]]:
+        g = lambda s: G[f"{name}/{s}"]  # noqa: E731
+        n = int(g("shape")[0])
+        if str(g("layout")) == "coo":
+            row, col = g("indices")
+        else:
+            crow, col = g("crow"), g("col")
+            row = np.repeat(np.arange(n), np.diff(crow))
+        X, Y = (g("x"), g("gradB")) if bool(g("transpose")) else (g("gradB"), g("x"))
+        got = -np.einsum("ek,ek->e", X[row], Y[col])
+        np.testing.assert_allclose(got, g("gradA_values"), rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(-orc.sddmm(row.astype(np.int64), col.astype(np.int64), X, Y), g("gradA_values"),
+                                   rtol=1e-12, atol=1e-12)

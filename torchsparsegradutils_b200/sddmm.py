@@ -42,3 +42,34 @@ def sddmm(A: torch.Tensor, X: torch.Tensor, Y: torch.Tensor) -> torch.Tensor:
     pat = csr_pattern(A)
     out = _ops.sddmm(pat, X, Y, None, pat.nnz_total)
     return out.view(A.values().shape)
+
+
+def solve_grad_A(A: torch.Tensor, gradB: torch.Tensor, x: torch.Tensor, transpose: bool = False) -> torch.Tensor:
+    """Sparse gradient of a linear solve ``A x = B`` (``A^T x = B`` if ``transpose``) w.r.t. A's stored entries.
+
+    ``gradA[i, j] = -<gradB[i, :], x[j, :]>``; with ``transpose``: ``-<gradB[j, :], x[i, :]>`` -- the step the
+    reference evaluates with ``repeat_interleave`` + two ``index_select`` + ``mul`` + ``sum`` in
+    ``SparseTriangularSolve.backward`` (``sparse_solve.py:216-235``), ``SparseGenericSolve.backward``
+    (``:487-504``) and the first term of ``SparseGenericLstsq.backward`` (``sparse_lstsq.py:239-246``), here one
+    fused SDDMM launch with no ``nnz x K`` temporaries.  ``gradB`` is the dense gradient the caller obtained from
+    its own (transposed) solve and ``x`` the forward solution, both ``(n, K)`` or ``(n,)``.  (The least-squares
+    backward adds a second sampled product, ``sddmm(A, B - A x, lstsq(A, gradB))``, ``sparse_lstsq.py:248-258``.)
+
+    Returns a sparse tensor with A's layout, shape and index tensors (CSR: A's own crow/col; COO: A's indices in
+    storage order), like the reference (``sparse_solve.py:237-240``, ``:510-513``).
+    """
+    if A.layout not in (torch.sparse_coo, torch.sparse_csr):
+        raise ValueError("A should be in either COO or CSR sparse format")
+    if A.dim() != 2:
+        raise ValueError("solve_grad_A expects a 2-D sparse matrix (split batched operands per item)")
+    if gradB.dim() == 1:
+        gradB = gradB.unsqueeze(-1)
+    if x.dim() == 1:
+        x = x.unsqueeze(-1)
+    vals = sddmm(A, x, gradB) if transpose else sddmm(A, gradB, x)
+    vals = vals.neg_()
+    if vals.dtype != A.dtype:
+        vals = vals.to(A.dtype)
+    if A.layout == torch.sparse_coo:
+        return torch.sparse_coo_tensor(A._indices(), vals, A.shape)
+    return torch.sparse_csr_tensor(A.crow_indices(), A.col_indices(), vals, A.shape)
