@@ -27,7 +27,11 @@
 #define TSGU_TILE_STAGE_BYTES 32768  // colind + vals bytes staged per tile and stage
 #endif
 #ifndef TSGU_TILE_ROWS
-#define TSGU_TILE_ROWS 128  // most rows a tile may hold; the launcher picks tile_rows <= this from nnz/row
+#define TSGU_TILE_ROWS 256  // capacity of the staged rowptr slice: most rows a tile may hold
+#endif
+#ifndef TSGU_TILE_ROWS_DEFAULT
+#define TSGU_TILE_ROWS_DEFAULT 128  // rows per tile the launchers ask for unless they pass their own bound (swept:
+                                    // 256 helps only the SDDMM with one vector per lane, config 3 0.688 -> 0.650 ms)
 #endif
 
 namespace tsgu {
@@ -85,12 +89,14 @@ struct TileCfg {
 
 // rows per tile for a launch: as many as fit the staging capacity with 25 % slack for uneven rows,
 // capped by TSGU_TILE_ROWS, and a multiple of the number of lane groups so every group gets whole rows
-inline int pick_tile_rows(int64_t total_rows, int64_t nnz_total, int cap_entries, int groups) {
+inline int pick_tile_rows(int64_t total_rows, int64_t nnz_total, int cap_entries, int groups,
+                          int max_rows = TSGU_TILE_ROWS_DEFAULT) {
+  if (max_rows > TSGU_TILE_ROWS) max_rows = TSGU_TILE_ROWS;
   const double avg = total_rows > 0 ? (double)nnz_total / (double)total_rows : 0.0;
-  int64_t r = avg > 0 ? (int64_t)((double)cap_entries / (1.25 * avg)) : TSGU_TILE_ROWS;
-  if (r > TSGU_TILE_ROWS) r = TSGU_TILE_ROWS;
+  int64_t r = avg > 0 ? (int64_t)((double)cap_entries / (1.25 * avg)) : max_rows;
+  if (r > max_rows) r = max_rows;
   r = r / groups * groups;
-  if (r < groups) r = groups < TSGU_TILE_ROWS ? groups : TSGU_TILE_ROWS;
+  if (r < groups) r = groups < max_rows ? groups : max_rows;
   return (int)r;
 }
 
