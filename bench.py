@@ -51,6 +51,13 @@ CONFIGS = {
     # benchmarks/results/sparse_mm_suite_results.csv:6: fwd 722 us, fwd+bwd 73.1 ms on an RTX 4090), random pattern
     "cfd2": dict(kind="csr_uniform", n=123440, m=123440, per_row=25, K=128, dtype="f32", batch=None,
                  desc="cfd2-sized synthetic CSR 123440^2, 25 nnz/row (3 086 000 nnz) x dense 123440x128 fp32"),
+    # the reference's own published random cases (RTX 4090, wall clock incl. clones), same sizes:
+    # benchmarks/results/sparse_mm_rand_results.csv:66 ("large": fwd 10.7 ms, fwd+bwd 33.6 ms) and
+    # batched_sparse_mm_rand_results.csv:31 (b=128: fwd 2.95 ms, fwd+bwd 11.8 ms)
+    "rand_large": dict(kind="coo_as_csr", n=262144, m=262144, nnz=65536, K=512, dtype="f32", batch=None, idx="i64",
+                       desc="reference 'large' random case: CSR int64 262144^2, nnz 65536 x dense 262144x512 fp32"),
+    "batched128": dict(kind="csr_uniform", n=1024, m=1024, per_row=4, K=64, dtype="f32", batch=128,
+                       desc="reference batched random case: batched CSR int32 b=128 1024^2, nnz 4096/item x dense 1024x64 fp32"),
     "5bf16": dict(kind="csr_uniform", n=262144, m=262144, per_row=8, K=512, dtype="bf16", batch=None,
                   desc="CSR 262144^2 8 nnz/row x dense 262144x512 bf16 (BASELINE configs[4])"),
 }
@@ -63,9 +70,13 @@ def build_inputs(cfg, device, batch_slice=None, seed_shift=0):
     dt = DT[cfg["dtype"]]
     if cfg["kind"] == "coo":
         A = W.uniform_coo(cfg["n"], cfg["m"], cfg["nnz"], dt, device, seed=1 + seed_shift)
+    elif cfg["kind"] == "coo_as_csr":  # uniformly random unique coordinates, handed over as CSR
+        A = W.uniform_coo(cfg["n"], cfg["m"], cfg["nnz"], dt, device, seed=1 + seed_shift).to_sparse_csr()
+        if cfg.get("idx") != "i64":
+            A = torch.sparse_csr_tensor(A.crow_indices().int(), A.col_indices().int(), A.values(), A.shape)
     elif cfg["kind"] == "csr_uniform":
-        A = W.uniform_rows_csr(cfg["batch"], cfg["n"], cfg["m"], cfg["per_row"], dt, torch.int32, device,
-                               seed=2 + seed_shift)
+        A = W.uniform_rows_csr(cfg["batch"], cfg["n"], cfg["m"], cfg["per_row"], dt,
+                               torch.int64 if cfg.get("idx") == "i64" else torch.int32, device, seed=2 + seed_shift)
     elif cfg["kind"] == "stencil":
         A = W.stencil27_csr(cfg["D"], dt, torch.int32, device, seed=3 + seed_shift)
     elif cfg["kind"] == "rmat":

@@ -39,7 +39,12 @@ def uniform_rows_csr(batch, n, m, per_row, dtype=torch.float32, index_dtype=torc
 def uniform_coo(n, m, nnz, dtype=torch.float32, device="cuda", seed=1):
     """Config 1: nnz unique coordinates uniform without replacement, coalesced COO (int64 indices)."""
     g = _gen(device, seed)
-    flat = torch.randperm(n * m, generator=g, device=device)[:nnz].sort().values
+    if n * m <= (1 << 28):
+        flat = torch.randperm(n * m, generator=g, device=device)[:nnz].sort().values
+    else:  # very sparse, huge index space: draw with replacement, drop the (rare) repeats, keep nnz of them
+        flat = torch.unique(torch.randint(0, n * m, (2 * nnz + 16,), generator=g, device=device, dtype=torch.int64))
+        flat = flat[torch.randperm(flat.numel(), generator=g, device=device)[:nnz]].sort().values
+        assert flat.numel() == nnz
     idx = torch.stack([flat // m, flat % m])
     vals = torch.rand(nnz, generator=g, device=device, dtype=torch.float32).to(dtype)
     return torch.sparse_coo_tensor(idx, vals, (n, m), is_coalesced=True)
