@@ -206,6 +206,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sharding", default="rows", choices=["rows", "k"],
+                    help="one large (unbatched) matrix at N > 1: rows = nnz-balanced row blocks, B replicated, grad_B "
+                         "all-reduce (north_star's scheme); k = dense columns split, A replicated, grad_A all-reduce")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="batched configs at N > 1: weak = every rank runs the full batch (global batch = batch x N); "
                          "strong = the batch items are split over the ranks")
@@ -266,7 +269,19 @@ def main():
     elif world == 1:
         scaling = args.scaling if cfg.get("batch") else "strong"
     A, B, G = build_inputs(cfg, dev, shard, seed_shift)
-    row_sharded = world > 1 and not cfg.get("batch") and A.layout == torch.sparse_csr
+    k_sharded = world > 1 and not cfg.get("batch") and args.sharding == "k"
+    row_sharded = world > 1 and not cfg.get("batch") and A.layout == torch.sparse_csr and not k_sharded
+    if k_sharded:
+        # one large matrix, alternative: shard the dense K columns; A replicated; forward and grad_B local,
+        # grad_A values all-reduced (nnz elements) over NVLink
+        from torchsparsegradutils_b200 import distributed as D
+
+        klo, khi = D.k_shard_bounds(cfg["K"], world, rank, align=16 // B.element_size())
+        assert khi > klo, "more ranks than 128-bit column blocks"
+        B = B[:, klo:khi].contiguous()
+        G = G[:, klo:khi].contiguous()
+        config_out["sharding"] = (f"dense columns K split over {world} ranks ({khi - klo} per rank), A replicated, "
+                                  "grad_A values all-reduce (NCCL)")
     if row_sharded:
         # one large matrix: nnz-balanced row blocks, B replicated, grad_B all-reduced over NVLink
         from torchsparsegradutils_b200 import distributed as D
@@ -288,7 +303,7 @@ def main():
     def step():
         A.grad = None
         B.grad = None
-        C = D.sparse_mm_row_sharded(A, B) if row_sharded else sparse_mm(A, B)
+        C = D.sparse_mm_row_sharded(A, B) if row_sharded else D.sparse_mm_k_sharded(A, B) if k_sharded else sparse_mm(A, B)
         C.backward(G)
         return C
 
@@ -367,7 +382,8 @@ def main():
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t)
-        cnt = torch.tensor([st["nnz"], launches], device=dev, dtype=torch.int64)
+        # K-sharding: every rank walks all nnz entries over its 1/N of the dense columns -- the job's units are nnz once
+        cnt = torch.tensor([0 if (k_sharded and rank != 0) else st["nnz"], launches], device=dev, dtype=torch.int64)
         dist.all_reduce(cnt)
         nnz_all, launches_all = int(cnt[0]), int(cnt[1])
     else:
@@ -408,7 +424,8 @@ def main():
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(A.detach(), B.detach(), G, args.e2e_steps, dev, dist,
-                      (lambda a, b: D.sparse_mm_row_sharded(a, b)) if row_sharded else sparse_mm)
+                      (lambda a, b: D.sparse_mm_row_sharded(a, b)) if row_sharded else
+                      (lambda a, b: D.sparse_mm_k_sharded(a, b)) if k_sharded else sparse_mm)
         e2e["value"] = (nnz_all / (e2e.pop("ms_per_step_max") * 1e-3))
 
     cpu_base = None

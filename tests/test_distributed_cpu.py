@@ -117,7 +117,61 @@ def _batch_sharded_worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("worker", [_row_sharded_worker, _batch_sharded_worker], ids=["row_sharded", "batch_sharded"])
+class _CpuSparseMM(torch.autograd.Function):
+    """Per-rank operator for the gloo tests: the reference's data flow on CPU (oracle/reference_port.py) with a
+    sparse gradient on A's pattern -- stands in for the CUDA sparse_mm, which cannot run here."""
+
+    @staticmethod
+    def forward(ctx, A, B):
+        ctx.save_for_backward(A, B)
+        return torch.sparse.mm(A.detach(), B.detach())
+
+    @staticmethod
+    def backward(ctx, G):
+        from oracle import reference_port as ref
+
+        A, B = ctx.saved_tensors
+        _, gA, gB = ref.forward_backward(A.detach(), B.detach(), G)
+        return torch.sparse_csr_tensor(A.crow_indices(), A.col_indices(), gA, A.shape), gB
+
+
+def test_k_shard_bounds_cover_and_align():
+    for K, align in ((512, 4), (10, 4), (128, 8), (7, 1), (3, 4)):
+        for world in (1, 2, 3, 8):
+            spans = [D.k_shard_bounds(K, world, r, align) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == K
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert all(lo % align == 0 for lo, _ in spans if lo < K)
+    with pytest.raises(ValueError):
+        D.k_shard_bounds(8, 2, 2)
+
+
+def _k_sharded_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        A, B, G = _problem(K=6)
+        lo, hi = D.k_shard_bounds(B.shape[1], world, rank)
+        Al = A.detach().requires_grad_(True)  # replicated sparse operand
+        Bl = B[:, lo:hi].clone().requires_grad_(True)
+        C_loc = D.sparse_mm_k_sharded(Al, Bl, local_mm=_CpuSparseMM.apply)
+        C_loc.backward(G[:, lo:hi].contiguous())
+        dense = A.to_dense()
+        ref_C, ref_gB = dense @ B, dense.t() @ G
+        ref_gA = (G @ B.t()) * (dense != 0)
+        # C and grad_B column blocks are local; every replica of A must hold the FULL sampled product
+        ok = (torch.allclose(C_loc, ref_C[:, lo:hi]) and torch.allclose(Bl.grad, ref_gB[:, lo:hi])
+              and torch.allclose(Al.grad.to_dense(), ref_gA) and torch.equal(Al.grad.col_indices(), A.col_indices()))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, bool(ok))
+        if rank == 0:
+            out.put(all(gathered))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("worker", [_row_sharded_worker, _batch_sharded_worker, _k_sharded_worker],
+                         ids=["row_sharded", "batch_sharded", "k_sharded"])
 def test_world_size_2_gloo(worker):
     ctx = mp.get_context("spawn")
     out = ctx.SimpleQueue()

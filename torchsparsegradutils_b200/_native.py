@@ -90,7 +90,14 @@ def launch_count() -> int:
     return int(lib().tsgu_launch_count())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr(device: torch.device) -> int:
+    """cudaStream_t of torch's current stream on `device` (the raw getter is ~30x cheaper than building a
+    torch.cuda.Stream object: 11 us -> 0.3 us of host time per launch)."""
+    if _raw_stream is not None and device.index is not None:
+        return _raw_stream(device.index)
     return torch.cuda.current_stream(device).cuda_stream
 
 
