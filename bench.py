@@ -206,7 +206,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--sharding", default="rows", choices=["rows", "k"],
+    ap.add_argument("--sharding", default="k", choices=["rows", "k"],
                     help="one large (unbatched) matrix at N > 1: rows = nnz-balanced row blocks, B replicated, grad_B "
                          "all-reduce (north_star's scheme); k = dense columns split, A replicated, grad_A all-reduce")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
