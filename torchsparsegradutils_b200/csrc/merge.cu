@@ -15,7 +15,7 @@
 #include "tile.cuh"
 
 #ifndef TSGU_MERGE_P
-#define TSGU_MERGE_P 2048
+#define TSGU_MERGE_P 3072  // path items per tile (swept on config 4 with 2 CTAs/SM: 1024 2.59, 2048 2.20, 3072 2.10, 4096 2.96 ms per SpMM)
 #endif
 #ifndef TSGU_MERGE_MINB
 #define TSGU_MERGE_MINB 2   // resident CTAs per SM the register allocation aims for (swept on config 4: 2 CTAs x 16 loads beat 3 x 8)
