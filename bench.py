@@ -196,6 +196,30 @@ def cpu_reference_run(cfg, steps, warmup, sample_note_only=False):
 
 
 # ------------------------------------------------------------------------------------- main
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU, before any pinned buffer is
+    allocated: with several ranks per node, first-touch then places the e2e leg's pinned staging buffers on the
+    GPU's own NUMA node instead of wherever the launcher happened to start the process (cross-socket PCIe traffic
+    is what limits the N > 1 e2e numbers).  Best effort: returns a description or None."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].isdigit() else local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus and len(cpus) < ncpu:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} CPUs local to GPU {idx}"
+    except Exception:  # noqa: BLE001 -- NVML missing / container without affinity rights: run unbound
+        return None
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -247,6 +271,9 @@ def main():
         from torchsparsegradutils_b200.csrc.build import build as _build_native
 
         _build_native(verbose=True)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    if numa:
+        config_out["host_affinity"] = numa
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
