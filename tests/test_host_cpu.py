@@ -165,3 +165,24 @@ def test_batch_sparse_mv_rank_errors():
     calls = []
     out = batch_sparse_mv(A, torch.ones(5, 3), op=lambda a, b: calls.append(tuple(b.shape)) or torch.zeros(3, 5))
     assert calls == [(3, 5)] and out.shape == (5, 3)  # (k, n) vectors go in as a (n, k) view, come back as (k, n)
+
+
+def test_uniform_rows_gate_of_k_slicing():
+    """`CsrPattern.uniform_rows` (gate of TSGU_ALGO_FLAG_KSLICE): longest row <= 1.25 x mean + 1, for the flat
+    layout our builders emit and for torch's batched (b, n+1) crow layout; empty patterns are never 'uniform'."""
+    import torch
+
+    from torchsparsegradutils_b200 import _native as nat
+    from torchsparsegradutils_b200._pattern import CsrPattern
+
+    def pat(rowptr, batch, n, bstride, nnz_total):
+        col = torch.zeros(max(nnz_total, 1), dtype=torch.int32)
+        return CsrPattern(rowptr, col, None, batch, n, 8, bstride, 0, nnz_total, nat.I32)
+
+    flat = torch.arange(0, 4 * 6 + 1, 4, dtype=torch.int32)  # 6 rows of exactly 4
+    assert pat(flat, 1, 6, 6, 24).uniform_rows
+    ragged = torch.tensor([0, 1, 1, 2, 20, 21, 24], dtype=torch.int32)  # one row of 18 among rows of 0-3
+    assert not pat(ragged, 1, 6, 6, 24).uniform_rows
+    batched = torch.stack([flat[:4], flat[:4]])  # torch batched CSR: (b, n+1) with per-item offsets
+    assert pat(batched, 2, 3, 4, 24).uniform_rows
+    assert not pat(torch.zeros(7, dtype=torch.int32), 1, 6, 6, 0).uniform_rows
