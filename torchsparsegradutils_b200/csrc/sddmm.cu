@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256, TSGU_TILE_MINB(VPL)) sddmm_tile_kernel(co
               const char* brow = Bb + (uint64_t)cj * row_bytes;
 #pragma unroll
               for (int w = 0; w < VPL; ++w) {
-                if (EXACT || on[w]) b[u][w] = __ldg(reinterpret_cast<const uint4*>(brow + w * (LPR * 16)));
+                if (EXACT || on[w]) b[u][w] = ldg_gather(reinterpret_cast<const uint4*>(brow + w * (LPR * 16)));
                 else b[u][w] = make_uint4(0, 0, 0, 0);
               }
             }
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256, TSGU_TILE_MINB(VPL)) sddmm_tile_kernel(co
               const char* brow = Bb + (uint64_t)cj * row_bytes;
 #pragma unroll
               for (int w = 0; w < VPL; ++w) {
-                if (j0 + u < cnt && (EXACT || on[w])) b[u][w] = __ldg(reinterpret_cast<const uint4*>(brow + w * (LPR * 16)));
+                if (j0 + u < cnt && (EXACT || on[w])) b[u][w] = ldg_gather(reinterpret_cast<const uint4*>(brow + w * (LPR * 16)));
                 else b[u][w] = make_uint4(0, 0, 0, 0);
               }
             }
