@@ -29,6 +29,9 @@
 #ifndef TSGU_MERGE_LOADS
 #define TSGU_MERGE_LOADS 16  // 128-bit dense-row loads in flight per lane (SpMM)
 #endif
+#ifndef TSGU_MERGE_SDDMM_PREFETCH
+#define TSGU_MERGE_SDDMM_PREFETCH 0  // 1: prefetch the next row of G in the merge-path SDDMM (experiment, see the kernel)
+#endif
 #ifndef TSGU_MERGE_SDDMM_LOADS
 #define TSGU_MERGE_SDDMM_LOADS 8  // ... and in the SDDMM, which wants more warps instead (row changes stall on a G-row fetch)
 #endif
@@ -638,6 +641,32 @@ __global__ void __launch_bounds__(256, TSGU_MERGE_SDDMM_MINB) sddmm_merge_kernel
         }
       };
       load_g();
+#if TSGU_MERGE_SDDMM_PREFETCH
+      // Experiment (off by default, not yet measured): keep the raw G row of the NEXT row that owns entries in
+      // flight while the current row is consumed, so a row change costs an unpack instead of a global-load stall.
+      Raw<V, EPV> gn[VPL];
+      int nrow = rowl;
+      const int rows_last = (int)(ti1 - ti0);  // last local row that can own entries of this tile
+      auto prefetch = [&]() {
+        int q = rowl + 1;
+        while (q <= rows_last && ti0 + q < p.rows && (int64_t)rp[q + 1] == (int64_t)rp[q]) ++q;  // empty rows
+        nrow = q;
+        const bool valid = q <= rows_last && ti0 + q < p.rows;
+        const V* Grow = p.G + (ti0 + (valid ? q : rowl)) * p.g_rs;
+#pragma unroll
+        for (int w = 0; w < VPL; ++w)
+          gn[w] = (EXACT || on[w]) ? raw_ldg<V, EPV>(Grow + (int64_t)(w * LPR + gl) * EPV) : raw_zero<V, EPV>();
+      };
+      prefetch();
+      auto next_row = [&](int eu) {  // entries are consecutive, so the row that owns `eu` is the prefetched one
+        (void)eu;
+        rowl = nrow;
+        row_end = local_end(rowl);
+#pragma unroll
+        for (int w = 0; w < VPL; ++w) raw_unpack<V, EPV>(gn[w], g[w]);
+        prefetch();
+      };
+#else
       auto next_row = [&](int eu) {  // skip empties, fetch that row of G
         do {
           ++rowl;
@@ -645,6 +674,7 @@ __global__ void __launch_bounds__(256, TSGU_MERGE_SDDMM_MINB) sddmm_merge_kernel
         } while (eu >= row_end);
         load_g();
       };
+#endif
       auto dot = [&](const uint4 (&bu)[VPL], Acc& out) {
 #pragma unroll
         for (int w = 0; w < VPL; ++w) {
