@@ -29,6 +29,11 @@
 #ifndef TSGU_MERGE_LOADS
 #define TSGU_MERGE_LOADS 16  // 128-bit dense-row loads in flight per lane (SpMM)
 #endif
+#ifndef TSGU_MERGE_HEAD_IN_REGS
+#define TSGU_MERGE_HEAD_IN_REGS 0  // 1: a group's head partial stays in its own registers (it is only ever read back by the
+                                   // same lanes), halving the partial buffers in shared memory -> room for larger tiles
+                                   // (experiment, not yet measured; sweep with TSGU_MERGE_P=4096)
+#endif
 #ifndef TSGU_MERGE_SDDMM_PREFETCH
 #define TSGU_MERGE_SDDMM_PREFETCH 0  // 1: prefetch the next row of G in the merge-path SDDMM (experiment, see the kernel)
 #endif
@@ -116,9 +121,13 @@ struct MergeSpmmSmem {
   static constexpr int GROUPS = 256 / LPR;
   static constexpr int KSLOT = LPR * VPL * (16 / (int)sizeof(V));  // accumulators per partial vector (>= K)
   MergeStage<V, I, VALS> st[2];
+#if !TSGU_MERGE_HEAD_IN_REGS
   alignas(16) Acc head[GROUPS][KSLOT];
+#endif
   alignas(16) Acc tail[GROUPS][KSLOT];
+#if !TSGU_MERGE_HEAD_IN_REGS
   int64_t head_row[GROUPS];
+#endif
   int64_t tail_row[GROUPS];
   alignas(8) uint64_t full[2];
 };
@@ -217,7 +226,16 @@ __global__ void __launch_bounds__(256, TSGU_MERGE_MINB) spmm_merge_kernel(const 
     int rowl = gi0l;
     int row_end = rowl < gi1l ? (int)((int64_t)rp[rowl + 1] - tj0) : INT_MAX;
     bool head = gi0 < p.rows && (int64_t)rp[gi0l] < gj0;  // the first row began before this group's range
+#if TSGU_MERGE_HEAD_IN_REGS
+    Acc hacc[VPL][EPV];
+    int64_t my_head_row = -1;
+#pragma unroll
+    for (int w = 0; w < VPL; ++w)
+#pragma unroll
+      for (int i = 0; i < EPV; ++i) hacc[w][i] = Acc(0);
+#else
     if (gl == 0) sm.head_row[group] = -1;
+#endif
     if (tid == 0) p.carry_row[t * 2 + 0] = -1;  // overwritten after the barrier if this tile has a head partial
 
     // finish the current row: interior rows go straight to C, a head row that began before this group's
@@ -227,8 +245,13 @@ __global__ void __launch_bounds__(256, TSGU_MERGE_MINB) spmm_merge_kernel(const 
 #pragma unroll
         for (int w = 0; w < VPL; ++w)
 #pragma unroll
+#if TSGU_MERGE_HEAD_IN_REGS
+          for (int i = 0; i < EPV; ++i) hacc[w][i] = acc[w][i];
+        my_head_row = gi0;
+#else
           for (int i = 0; i < EPV; ++i) sm.head[group][(w * LPR + gl) * EPV + i] = acc[w][i];
         if (gl == 0) sm.head_row[group] = gi0;
+#endif
         head = false;
       } else {
         V* Crow = p.C + (ti0 + rowl) * p.ldc;
@@ -324,7 +347,11 @@ __global__ void __launch_bounds__(256, TSGU_MERGE_MINB) spmm_merge_kernel(const 
 
     // ---- ordered combine of rows cut by group boundaries --------------------------------
     {
+#if TSGU_MERGE_HEAD_IN_REGS
+      const int64_t hr = my_head_row;
+#else
       const int64_t hr = sm.head_row[group];
+#endif
       if (hr >= 0) {
         int glo = group;
         while (glo > 0 && sm.tail_row[glo - 1] == hr) --glo;
@@ -341,7 +368,11 @@ __global__ void __launch_bounds__(256, TSGU_MERGE_MINB) spmm_merge_kernel(const 
 #pragma unroll
         for (int w = 0; w < VPL; ++w)
 #pragma unroll
+#if TSGU_MERGE_HEAD_IN_REGS
+          for (int i = 0; i < EPV; ++i) tot[w][i] += hacc[w][i];
+#else
           for (int i = 0; i < EPV; ++i) tot[w][i] += sm.head[group][(w * LPR + gl) * EPV + i];
+#endif
         const bool from_earlier_tile = (glo == 0) && ((int64_t)rp[(int)(hr - ti0)] < tj0);
         if (from_earlier_tile) {  // completed by the fix-up kernel together with earlier tiles' tails
           Acc* dst = p.carry + (t * 2 + 0) * p.kpad;
