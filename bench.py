@@ -220,7 +220,31 @@ def bind_to_gpu_numa_node(local_rank: int):
     return None
 
 
+_JSON_FD = None
+
+
+def _route_library_chatter_to_stderr():
+    """Keep stdout for the ONE JSON line: anything a library writes to fd 1 while the bench runs (NCCL's version
+    banner under torchrun, for one) is sent to stderr instead; emit_json() writes to the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _route_library_chatter_to_stderr()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -259,7 +283,7 @@ def main():
                 "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit_json(line)
         return
 
     # ------------------------------------------------------------------------- B200 arm
@@ -470,7 +494,7 @@ def main():
                 "kernels": kernels, "nnz_per_step": nnz_all,
                 "host_enqueue_ms_per_step": host_ms, "cold_first_step_ms": cold_ms,
                 "cold_pattern_step_ms": cold_pattern_ms}
-        print(json.dumps(line))
+        emit_json(line)
     if dist is not None:
         dist.destroy_process_group()
 
