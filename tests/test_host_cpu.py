@@ -186,3 +186,28 @@ def test_uniform_rows_gate_of_k_slicing():
     batched = torch.stack([flat[:4], flat[:4]])  # torch batched CSR: (b, n+1) with per-item offsets
     assert pat(batched, 2, 3, 4, 24).uniform_rows
     assert not pat(torch.zeros(7, dtype=torch.int32), 1, 6, 6, 0).uniform_rows
+
+
+def test_bench_stdout_carries_only_the_json_line(tmp_path):
+    """bench.py's contract: ONE JSON line on stdout.  Anything else written to fd 1 while it runs (NCCL prints its
+    version banner there under torchrun) must end up on stderr."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "emit.py"
+    script.write_text(
+        "import os, sys\\n"
+        f"sys.path.insert(0, {root!r})\\n"
+        "import bench\\n"
+        "bench._route_library_chatter_to_stderr()\\n"
+        "os.write(1, b'NCCL version banner\\\\n')\\n"
+        "print('python-level chatter')\\n"
+        "bench.emit_json({'metric': 'm', 'value': 1})\\n")
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1 and json.loads(lines[0]) == {"metric": "m", "value": 1}
+    assert "NCCL version banner" in r.stderr and "python-level chatter" in r.stderr
