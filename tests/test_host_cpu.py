@@ -198,14 +198,15 @@ def test_bench_stdout_carries_only_the_json_line(tmp_path):
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = tmp_path / "emit.py"
-    script.write_text(
-        "import os, sys\\n"
-        f"sys.path.insert(0, {root!r})\\n"
-        "import bench\\n"
-        "bench._route_library_chatter_to_stderr()\\n"
-        "os.write(1, b'NCCL version banner\\\\n')\\n"
-        "print('python-level chatter')\\n"
-        "bench.emit_json({'metric': 'm', 'value': 1})\\n")
+    script.write_text("\n".join([
+        "import os, sys",
+        f"sys.path.insert(0, {root!r})",
+        "import bench",
+        "bench._route_library_chatter_to_stderr()",
+        "os.write(1, b'NCCL version banner' + bytes([10]))",
+        "print('python-level chatter')",
+        "bench.emit_json({'metric': 'm', 'value': 1})",
+    ]) + "\n")
     r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
