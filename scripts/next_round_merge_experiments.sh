@@ -22,6 +22,9 @@ case "$1" in
       echo "== parity $lib"
       TSGU_B200_LIB=$PWD/$lib python -m pytest tests/test_sparse_mm_gpu.py -q -x -k merge 2>&1 | tail -1
     done | tee gpurun_out/merge_variants_parity.txt
-    bash scripts/merge_variant_sweep.sh 2>&1 | tee gpurun_out/merge_variants_sweep.txt ;;
+    bash scripts/merge_variant_sweep.sh 2>&1 | tee gpurun_out/merge_variants_sweep.txt
+    # host-side experiment: value gather of the transposed pass on a side stream, overlapped with the SDDMM
+    echo "== overlap gather: parity"; TSGU_B200_OVERLAP_GATHER=1 python -m pytest tests/test_sparse_mm_gpu.py tests/test_golden_gpu.py -q -x 2>&1 | tail -1
+    for v in 0 1; do echo "== TSGU_B200_OVERLAP_GATHER=$v"; TSGU_B200_OVERLAP_GATHER=$v CONFIGS="2 3" bash scripts/bench_all_configs.sh; done 2>&1 | tee gpurun_out/overlap_gather.txt ;;
   *) echo "usage: $0 build|run"; exit 2 ;;
 esac

@@ -165,9 +165,15 @@ def _l2_bytes(dev: torch.device) -> int:
     return _L2_BYTES[key]
 
 
+def wants_pregather(pat: CsrPattern) -> bool:
+    """True when spmm() would first put the values into the pattern's own order (one streaming pass)."""
+    return pat.perm is not None and pat.nnz_total >= _PREGATHER_MIN_NNZ and pat.algo != nat.ALGO_SPLIT
+
+
 def spmm(pat: CsrPattern, vals: torch.Tensor, dense: torch.Tensor, algo: Optional[int] = None,
-         tag: str = "spmm") -> torch.Tensor:
-    """out[t] = A[t] @ dense[t]; dense is (batch, m, K) (any strides); returns contiguous (batch, n, K)."""
+         tag: str = "spmm", vals_in_pattern_order: bool = False) -> torch.Tensor:
+    """out[t] = A[t] @ dense[t]; dense is (batch, m, K) (any strides); returns contiguous (batch, n, K).
+    `vals_in_pattern_order`: `vals` were already gathered through `pat.perm` by the caller (gather_values)."""
     algo = pat.algo if algo is None else algo
     if algo == nat.ALGO_SPLIT:
         d3 = prepare_dense(_as3d(dense))
@@ -182,7 +188,7 @@ def spmm(pat: CsrPattern, vals: torch.Tensor, dense: torch.Tensor, algo: Optiona
     dev = dense.device
     L = nat.lib()
     vdt = nat.val_enum(dense.dtype)
-    perm = pat.perm
+    perm = None if vals_in_pattern_order else pat.perm
     if perm is not None and pat.nnz_total >= _PREGATHER_MIN_NNZ:
         # one streaming pass that puts the values in the structure's own order is cheaper than a
         # divergent 4-byte gather per entry inside the bandwidth-critical SpMM (0.37 -> 0.25+0.03 ms on config 2)
