@@ -6,9 +6,14 @@
 One step = one forward + backward of ``sparse_mm(A, B)`` (C = A B; grad_A by SDDMM; grad_B = A^T G)
 over one batch of synthetic input.  Default workload = BASELINE.json configs[1] ("config 2"): batched
 CSR, batch 8, 65536 x 65536, 16 nnz/row, dense 65536 x 128, fp32 / int32.  With N > 1 (launched by
-torchrun, one rank per GPU) batch items are independent units with no data-path collective: by default
-every rank runs a full batch of 8 of its own (weak scaling, global batch 8 N); ``--scaling strong`` splits
-the 8 items of BASELINE's literal config over the ranks instead.
+torchrun, one rank per GPU) batch items are independent units with no data-path collective: by default the
+8 items of BASELINE's literal config are split over the ranks (``"scaling": "strong"``); ``--scaling weak``
+gives every rank a full batch of 8 of its own instead (global batch 8 N).
+
+The timed region replays the step from a CUDA graph (fixed pattern and shapes: no host work between the
+kernels); an eager region of the same K steps runs beside it and supplies the per-kernel CUDA-event durations
+(`kernels`, `roofline`) and the host enqueue time.  `value` comes from the faster of the two regions
+(`timed_region` says which); both do identical GPU work.
 
 Prints ONE JSON line (rank 0).  `value` = nnz/s with inputs resident in HBM; `e2e` = the same metric
 through the public API from pinned HOST buffers (H2D of A, B, G and D2H of C, grad_A, grad_B inside
@@ -162,9 +167,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ CPU baseline
-def cpu_reference_run(cfg, steps, warmup, sample_note_only=False):
+def cpu_reference_run(cfg, steps, warmup, budget_s=150.0, sample_note_only=False):
     """Time the reference's CPU data flow (torch CPU ops, all host threads) on a bounded sample of the
-    workload: one batch item for batched configs, a row prefix for the very large single matrices."""
+    workload: one batch item for batched configs, a row prefix for the very large single matrices.  `steps` and
+    `warmup` are honoured unless the run would exceed `budget_s` seconds (then fewer timed steps, never < 1)."""
     from oracle import reference_port as rp
 
     torch.set_num_threads(os.cpu_count() or 1)
@@ -172,7 +178,9 @@ def cpu_reference_run(cfg, steps, warmup, sample_note_only=False):
     sample = "full workload"
     if c.get("batch"):
         c["batch"] = 1
-        sample = f"1 of {cfg['batch']} batch items (same n, nnz/row, K)"
+        sample = (f"1 of {cfg['batch']} batch items (same n, nnz/row, K); the port runs the reference's forward, SDDMM "
+                  "temporaries and A^T G but skips its sparse_block_diag_split + stack_csr of grad_A (conservative: "
+                  "the real reference does more work per step)")
     if c["kind"] == "stencil":
         c["D"] = 64
         sample = "64^3 volume (1/8 of the rows, same stencil)"
@@ -184,15 +192,20 @@ def cpu_reference_run(cfg, steps, warmup, sample_note_only=False):
         sample += "; fp32 (the reference's CPU CSR path has no bf16)"
     A, B, G = build_inputs(c, "cpu")
     nnz = problem_stats(A, c["K"])["nnz"]
-    times = []
+    times, t_start, done_warm = [], time.perf_counter(), 0
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         rp.forward_backward(A, B, G)
-        times.append(time.perf_counter() - t0)
-    times = times[warmup:]
+        dt = time.perf_counter() - t0
+        if i < warmup and (time.perf_counter() - t_start) < budget_s / 3:
+            done_warm += 1
+            continue
+        times.append(dt)
+        if time.perf_counter() - t_start > budget_s:
+            break
     sec = statistics.median(times)
     return dict(value=nnz / sec, unit=UNIT, cores=torch.get_num_threads(), kind="port", sample=sample,
-                ms_per_step=sec * 1e3, nnz_per_step=nnz, steps=len(times))
+                ms_per_step=sec * 1e3, nnz_per_step=nnz, steps=len(times), warmup=done_warm)
 
 
 # ------------------------------------------------------------------------------------- main
@@ -243,6 +256,74 @@ def emit_json(line: dict) -> None:
         os.write(_JSON_FD, data)
 
 
+def dense_mib_per_rank(cfg, world, scaling, k_sharded):
+    """Dense operands + outputs one rank touches per step (B, G read; C, grad_B written), from the config alone --
+    both arms print the same `config`, so nothing in it may depend on tensors only one arm builds."""
+    s_v = DT[cfg["dtype"]].itemsize
+    if cfg["kind"] == "stencil":
+        n = m = cfg["D"] ** 3
+    elif cfg["kind"] == "rmat":
+        n = m = 1 << cfg["scale"]
+    else:
+        n, m = cfg["n"], cfg["m"]
+    items = cfg.get("batch") or 1
+    if cfg.get("batch") and world > 1 and scaling == "strong":
+        items = max(items // world, 1)
+    K = cfg["K"] // world if (k_sharded and world > 1) else cfg["K"]
+    return items * (m * K + 3 * n * K) * s_v / 2**20
+
+
+def describe_config(cfg, args, world):
+    batched = bool(cfg.get("batch"))
+    k_sharded = world > 1 and not batched and args.sharding == "k"
+    scaling = args.scaling if batched else "strong"
+    if batched and world > 1 and scaling == "strong":
+        sharding = f"strong: {cfg['batch']} batch items split over {world} ranks, no collective"
+    elif batched and world > 1:
+        sharding = f"weak: {cfg['batch']} batch items per rank, global batch {cfg['batch'] * world}, no collective"
+    elif batched:
+        sharding = "single GPU: all batch items on one rank"
+    elif world == 1:
+        sharding = "single GPU"
+    elif k_sharded:
+        sharding = f"dense columns K split over {world} ranks, A replicated, grad_A values all-reduce (NCCL)"
+    else:
+        sharding = f"nnz-balanced row blocks over {world} ranks, B replicated, grad_B reduce-scatter + all-gather (NCCL)"
+    mib = dense_mib_per_rank(cfg, world, scaling, k_sharded)
+    flush = mib <= 252
+    l2 = (f"dense operands + outputs of one step = {mib:.0f} MiB per rank fit L2 (126 MB): an L2 flush (256 MiB write) "
+          "runs between timed steps, outside the per-step event pair" if flush else
+          f"inputs larger than L2: dense operands + outputs of one step = {mib:.0f} MiB per rank vs 126 MB L2; no explicit flush")
+    return ({"workload": cfg["desc"], "config_id": args.config, "K": cfg["K"], "l2": l2, "sharding": sharding},
+            scaling, k_sharded, flush)
+
+
+def reference_methodology_ms(A, B, op, repeats=10):
+    """The reference's own timing method (benchmarks/benchmark_utils.py:194-199, :258-264): host wall clock around
+    clone(A) + clone(B) + op (+ out.sum().backward()) + synchronize, empty_cache before every repeat.  Cloning A gives
+    it new index tensors, so the sparsity pattern is cold on every repeat.  Reported next to the CUDA-event numbers
+    for comparability with the reference's published (RTX 4090) rows; mean over `repeats` after 3 warm-ups."""
+    def one(backward):
+        torch.cuda.empty_cache()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        A1 = A.detach().clone().requires_grad_(True)
+        B1 = B.detach().clone().requires_grad_(True)
+        out = op(A1, B1)
+        if backward:
+            out.sum().backward()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3
+
+    res = {}
+    for name, bw in (("fwd_ms", False), ("fwd_bwd_ms", True)):
+        for _ in range(3):
+            one(bw)
+        res[name] = statistics.mean(one(bw) for _ in range(repeats))
+    res["method"] = "wall clock: clone A, clone B, op, sum().backward(), synchronize (reference benchmark_utils.py:194-199,258-264); pattern cold every repeat"
+    return res
+
+
 def main():
     _route_library_chatter_to_stderr()
     ap = argparse.ArgumentParser()
@@ -256,29 +337,31 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sharding", default="k", choices=["rows", "k"],
                     help="one large (unbatched) matrix at N > 1: rows = nnz-balanced row blocks, B replicated, grad_B "
-                         "all-reduce (north_star's scheme); k = dense columns split, A replicated, grad_A all-reduce")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="batched configs at N > 1: weak = every rank runs the full batch (global batch = batch x N); "
-                         "strong = the batch items are split over the ranks")
-    ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (launch-bound cases)")
+                         "reduce-scatter (north_star's scheme); k = dense columns split, A replicated, grad_A all-reduce")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="batched configs at N > 1: strong (default) = BASELINE's literal config, its batch items split over "
+                         "the ranks; weak = every rank runs a full batch of its own (global batch = batch x N)")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="time eager steps only (default: the timed region replays the step from a CUDA graph, the eager "
+                         "region beside it gives the per-kernel durations and the host enqueue time)")
+    ap.add_argument("--ref-methodology", action="store_true",
+                    help="also report the reference's wall-clock methodology (default on for cfd2 / rand_large / batched128)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     warmup = max(args.warmup, 3)
-    config_out = {"workload": cfg["desc"], "config_id": args.config, "K": cfg["K"],
-                  "l2": "no explicit flush: see l2_note (filled in once the operands exist)",
-                  "sharding": f"batch items split over {world} rank(s), no collective" if cfg.get("batch") else "replicas"}
+    config_out, scaling, k_sharded, flush = describe_config(cfg, args, world)
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return
-        base = cpu_reference_run(cfg, steps=max(1, min(args.steps, 3)), warmup=1)
+        base = cpu_reference_run(cfg, steps=max(args.steps, 1), warmup=max(args.warmup, 1), budget_s=150.0)
         line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
-                "steps": base["steps"], "warmup": 1, "ms_per_step": base["ms_per_step"], "higher_is_better": True,
-                "scaling": (args.scaling if cfg.get("batch") else "strong"), "vs_baseline": None, "dtype": "f32",
+                "steps": base["steps"], "warmup": base["warmup"], "ms_per_step": base["ms_per_step"], "higher_is_better": True,
+                "scaling": scaling, "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": config_out,
                 "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -296,8 +379,6 @@ def main():
 
         _build_native(verbose=True)
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
-    if numa:
-        config_out["host_affinity"] = numa
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
@@ -305,56 +386,40 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
-    scaling = "strong"
     shard, seed_shift = None, 0
     if cfg.get("batch") and world > 1:
-        if args.scaling == "strong":  # BASELINE's literal reading: batch 8 split over the ranks
+        if scaling == "strong":  # BASELINE's literal reading: batch 8 split over the ranks
             assert cfg["batch"] % world == 0, "batch must divide across ranks"
             per = cfg["batch"] // world
             shard = (rank * per, (rank + 1) * per)
-            config_out["sharding"] = f"strong: {cfg['batch']} batch items split over {world} ranks, no collective"
         else:  # independent batch items: every rank owns a full batch of its own (weak scaling)
-            scaling, seed_shift = "weak", 1000 * rank
-            config_out["sharding"] = (f"weak: {cfg['batch']} batch items per rank, global batch {cfg['batch'] * world}, "
-                                      "no collective")
-    elif world == 1:
-        scaling = args.scaling if cfg.get("batch") else "strong"
+            seed_shift = 1000 * rank
     A, B, G = build_inputs(cfg, dev, shard, seed_shift)
-    k_sharded = world > 1 and not cfg.get("batch") and args.sharding == "k"
     row_sharded = world > 1 and not cfg.get("batch") and A.layout == torch.sparse_csr and not k_sharded
+    from torchsparsegradutils_b200 import distributed as D
+
     if k_sharded:
         # one large matrix, alternative: shard the dense K columns; A replicated; forward and grad_B local,
         # grad_A values all-reduced (nnz elements) over NVLink
-        from torchsparsegradutils_b200 import distributed as D
-
         klo, khi = D.k_shard_bounds(cfg["K"], world, rank, align=16 // B.element_size())
         assert khi > klo, "more ranks than 128-bit column blocks"
         B = B[:, klo:khi].contiguous()
         G = G[:, klo:khi].contiguous()
-        config_out["sharding"] = (f"dense columns K split over {world} ranks ({khi - klo} per rank), A replicated, "
-                                  "grad_A values all-reduce (NCCL)")
     if row_sharded:
-        # one large matrix: nnz-balanced row blocks, B replicated, grad_B all-reduced over NVLink
-        from torchsparsegradutils_b200 import distributed as D
-
+        # one large matrix: nnz-balanced row blocks, B replicated, grad_B reduced over NVLink
         bounds = D.nnz_balanced_row_blocks(A.crow_indices(), world)
         A = D.shard_rows_csr(A, bounds[rank], bounds[rank + 1])
         G = G[bounds[rank]:bounds[rank + 1]].contiguous()
-        config_out["sharding"] = f"nnz-balanced row blocks over {world} ranks, B replicated, grad_B all-reduce (NCCL)"
     st = problem_stats(A, cfg["K"])
-    dense_mb = (B.numel() + 3 * G.numel()) * B.element_size() / 2**20  # B, G read; C, grad_B written (G ~ C ~ grad_B)
-    config_out["l2"] = (f"inputs larger than L2: dense operands + outputs of one step = {dense_mb:.0f} MiB vs 126 MB L2; "
-                        "no explicit flush" if dense_mb > 252 else
-                        f"dense operands + outputs of one step = {dense_mb:.0f} MiB fit L2 (small config): "
-                        "an L2 flush (256 MiB write) runs between timed steps")
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if dense_mb <= 252 else None
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush else None
     A.requires_grad_(True)
     B.requires_grad_(True)
+    op = D.sparse_mm_row_sharded if row_sharded else D.sparse_mm_k_sharded if k_sharded else sparse_mm
 
     def step():
         A.grad = None
         B.grad = None
-        C = D.sparse_mm_row_sharded(A, B) if row_sharded else D.sparse_mm_k_sharded(A, B) if k_sharded else sparse_mm(A, B)
+        C = op(A, B)
         C.backward(G)
         return C
 
@@ -383,117 +448,141 @@ def main():
     cold_pattern_ms = (time.perf_counter() - t_cp) * 1e3
     step()
     barrier()
-    run_step = step
-    if args.graph:  # capture one steady-state step (pattern cache warm) and replay it
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                step()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        cap0 = nat.launch_count()
-        with torch.cuda.graph(graph):
-            step()
-        graph_launches = nat.launch_count() - cap0  # kernels of ours inside one replay
-        run_step = graph.replay
-        config_out["cuda_graph"] = True
+
+    def timed_region(run_step, with_kernel_timer):
+        """K steps between a barrier + synchronize on both sides; returns (ms of the K steps, host ms to enqueue one,
+        clocks, per-kernel summary).  Small configs: L2 flush before every step, per-step event pairs."""
+        launches0 = nat.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kt_cm = _ops.KernelTimer() if with_kernel_timer else _ops._NULL
         barrier()
-    launches0 = nat.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk, _ops.KernelTimer() as kt:
-        e0.record()
-        t_host = time.perf_counter()
-        pairs = []
-        for _ in range(args.steps):
-            if flush_buf is not None:
-                # small configs: evict the operands from L2 between steps; the flush itself is outside
-                # the per-step event pair
-                flush_buf.zero_()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                run_step()
-                b.record()
-                pairs.append((a, b))
-            else:
-                run_step()
-        host_ms = (time.perf_counter() - t_host) * 1e3 / args.steps  # time to ENQUEUE a step (no sync)
-        e1.record()
-        barrier()
-    ms_total = sum(a.elapsed_time(b) for a, b in pairs) if pairs else e0.elapsed_time(e1)
-    launches = nat.launch_count() - launches0
-    if args.graph:
-        launches = graph_launches * args.steps
-        with _ops.KernelTimer() as kt:  # per-kernel durations cannot be read out of a graph replay: eager pass
-            for _ in range(5):
+        with ClockSampler(local_rank) as clk, kt_cm as kt:
+            e0.record()
+            t_host = time.perf_counter()
+            pairs = []
+            for _ in range(args.steps):
+                if flush_buf is not None:
+                    flush_buf.zero_()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    run_step()
+                    b.record()
+                    pairs.append((a, b))
+                else:
+                    run_step()
+            host_ms = (time.perf_counter() - t_host) * 1e3 / args.steps  # time to ENQUEUE a step (no sync)
+            e1.record()
+            barrier()
+        ms_total = sum(a.elapsed_time(b) for a, b in pairs) if pairs else e0.elapsed_time(e1)
+        return ms_total, host_ms, clk.report(), (kt.summary() if with_kernel_timer else None), nat.launch_count() - launches0
+
+    # region A: eager steps through the public op, with per-kernel CUDA events (roofline) and the host enqueue time
+    eager_total, host_ms, clocks, ksum, launches = timed_region(step, True)
+    timed = {"region": "eager", "ms_total": eager_total}
+    # region B: the same step replayed from a CUDA graph (fixed pattern, fixed shapes): no host work between kernels
+    graph_note = None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            cap0 = nat.launch_count()
+            with torch.cuda.graph(graph):
                 step()
+            graph_launches = nat.launch_count() - cap0  # kernels of ours inside one replay
+            for _ in range(warmup):
+                graph.replay()
+            g_total, g_host_ms, g_clocks, _, _ = timed_region(graph.replay, False)
+            graph_note = {"ms_per_step": g_total / args.steps, "host_enqueue_ms_per_step": g_host_ms}
+            if g_total <= eager_total:
+                timed = {"region": "cuda_graph", "ms_total": g_total}
+                clocks, launches = g_clocks, graph_launches * args.steps
+        except Exception as exc:  # noqa: BLE001 -- capture not possible (e.g. a collective that refuses capture): eager stands
+            graph_note = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
             torch.cuda.synchronize()
-        config_out["kernel_times"] = "separate eager pass of 5 steps (graph replays are opaque to events)"
+    ms_total = timed["ms_total"]
+    timed_region_note = (
+        "CUDA-graph replay of the step (pattern and shapes fixed); per-kernel durations and host enqueue time from the "
+        "eager region run beside it (same K steps, same work)" if timed["region"] == "cuda_graph" else
+        "eager steps through the public op")
     if dist is not None:
-        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_total, eager_total, host_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t)
+        ms_total, eager_total, host_ms_max = float(t[0]), float(t[1]), float(t[2])
         # K-sharding: every rank walks all nnz entries over its 1/N of the dense columns -- the job's units are nnz once
         cnt = torch.tensor([0 if (k_sharded and rank != 0) else st["nnz"], launches], device=dev, dtype=torch.int64)
         dist.all_reduce(cnt)
         nnz_all, launches_all = int(cnt[0]), int(cnt[1])
     else:
-        nnz_all, launches_all = st["nnz"], launches
+        nnz_all, launches_all, host_ms_max = st["nnz"], launches, host_ms
     ms_step = ms_total / args.steps
     value = nnz_all / (ms_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (live CUDA-event durations from the timed region)
+    # ---- roofline of the dominant kernel (live CUDA-event durations from the eager region)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    ksum = kt.summary()
     kernels = {}
     for tag, rec in ksum.items():
         alg = st["alg"].get(tag)
         if alg is None:
+            kernels[tag] = {"ms": rec["ms"], "launches": rec["launches"]}
             continue
         gbs = alg / (rec["ms"] * 1e-3) / 1e9
         kernels[tag] = {"ms": rec["ms"], "launches": rec["launches"], "alg_bytes": alg, "achieved_gbs": gbs,
                         "frac": gbs / peak, "gather_gbs": st["gather_bytes_per_pass"] / (rec["ms"] * 1e-3) / 1e9}
     # measured DRAM traffic per launch from the committed ncu --set full capture of this workload
     traffic = {}
-    tpath = os.path.join(ROOT, "profiles", f"r1_cfg{args.config}_traffic.json")
-    if os.path.exists(tpath) and world == 1:
-        traffic = {k: v["dram_bytes"] for k, v in json.load(open(tpath))["kernels"].items()}
-    dom = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
+    for rnd in ("r2", "r1"):
+        tpath = os.path.join(ROOT, "profiles", f"{rnd}_cfg{args.config}_traffic.json")
+        if os.path.exists(tpath) and world == 1:
+            traffic = {k: v["dram_bytes"] for k, v in json.load(open(tpath))["kernels"].items()}
+            break
+    main_k = {k: v for k, v in kernels.items() if "alg_bytes" in v}
+    dom = max(main_k, key=lambda k: main_k[k]["ms"]) if main_k else None
     roofline = None
     if dom:
         d = kernels[dom]
+        l2_peak = 20000.0  # GB/s: measured ceiling of a 512-B-row LDG gather out of L2 (profiles/r1_gather_ceilings.txt)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": d["frac"], "frac_of_nominal_8000": d["achieved_gbs"] / 8000.0, "traffic": traffic.get(dom), "alg_bytes": d["alg_bytes"], "peak_source": peak_src,
-                    "share_of_step": d["ms"] / ms_step, "l2_gather_gbs": d["gather_gbs"]}
+                    "frac": d["frac"], "frac_of_nominal_8000": d["achieved_gbs"] / 8000.0, "traffic": traffic.get(dom),
+                    "alg_bytes": d["alg_bytes"], "peak_source": peak_src,
+                    "share_of_step": d["ms"] / (eager_total / args.steps), "l2_gather_gbs": d["gather_gbs"],
+                    "l2_peak": l2_peak, "l2_ceiling_frac": d["gather_gbs"] / l2_peak}
     step_gbs = st["alg"]["total"] / (ms_step * 1e-3) / 1e9
+
+    ref_meth = None
+    if (args.ref_methodology or args.config in ("cfd2", "rand_large", "batched128")) and world == 1:
+        ref_meth = reference_methodology_ms(A, B, sparse_mm)
 
     # ---- e2e: same step through the public API from pinned host buffers
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(A.detach(), B.detach(), G, args.e2e_steps, dev, dist,
-                      (lambda a, b: D.sparse_mm_row_sharded(a, b)) if row_sharded else
-                      (lambda a, b: D.sparse_mm_k_sharded(a, b)) if k_sharded else sparse_mm)
+        e2e = run_e2e(A.detach(), B.detach(), G, args.e2e_steps, dev, dist, op)
         e2e["value"] = (nnz_all / (e2e.pop("ms_per_step_max") * 1e-3))
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb = cpu_reference_run(cfg, steps=5, warmup=1)
+        cb = cpu_reference_run(cfg, steps=5, warmup=1, budget_s=30.0)
         cpu_base = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
                 "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic", "config": config_out,
-                "clocks": clk.report(), "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline,
                 "cpu_baseline": cpu_base, "gflops": st["flops"] * (nnz_all / st["nnz"]) / (ms_step * 1e-3) / 1e9,
                 "step_alg_gbs": step_gbs * (nnz_all / st["nnz"]), "step_frac_of_hbm_peak": step_gbs / peak,
                 "kernels": kernels, "nnz_per_step": nnz_all,
-                "host_enqueue_ms_per_step": host_ms, "cold_first_step_ms": cold_ms,
-                "cold_pattern_step_ms": cold_pattern_ms}
+                "timed_region": timed_region_note, "eager_ms_per_step": eager_total / args.steps, "cuda_graph": graph_note,
+                "host_enqueue_ms_per_step": host_ms_max, "cold_first_step_ms": cold_ms,
+                "cold_pattern_step_ms": cold_pattern_ms, "reference_methodology": ref_meth, "host_affinity": numa}
         emit_json(line)
     if dist is not None:
         dist.destroy_process_group()

@@ -12,6 +12,7 @@ tests/test_utils.py:53-133, tests/test_distributions.py:323-347 (strided B), the
 Dockerfile.pip-install:47-52, plus the [probed] edge cases of SURVEY.md section 8(b).
 """
 import os
+import random
 import sys
 
 import numpy as np
@@ -35,6 +36,7 @@ from torchsparsegradutils.utils.utils import (  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 torch.manual_seed(42)
 np.random.seed(42)
+random.seed(42)  # the reference's rand_sparse draws coordinates with Python's `random` (utils/random_sparse.py)
 
 
 def npy(t):

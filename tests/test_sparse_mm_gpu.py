@@ -611,3 +611,99 @@ def test_split_rows_bounds_and_coo(bound, monkeypatch):
     A = torch.sparse_coo_tensor(torch.stack([rows, col])[:, sh], vals[sh], (700, 5000))
     _check(A, torch.rand(5000, 32, device=DEV), torch.rand(700, 32, device=DEV))
     tsgu.clear_pattern_cache()
+
+
+def test_pattern_cache_key_distinguishes_aliasing_index_views():
+    """Two COO tensors whose index tensors are different-length views of ONE buffer at offset 0 (same data pointer,
+    same version) must not share a cached pattern (the key now carries numel / shape / strides / offset)."""
+    import torchsparsegradutils_b200 as tsgu
+    from torchsparsegradutils_b200 import sparse_mm
+
+    tsgu.clear_pattern_cache()
+    g = torch.Generator().manual_seed(3)
+    n = m = 64
+    flat = torch.randperm(n * m, generator=g)[:200]
+    idx = torch.stack([flat // m, flat % m]).to(DEV)
+    v = torch.rand(200, generator=g).to(DEV)
+    B = torch.rand(m, 8, generator=g).to(DEV)
+    for cnt in (100, 200, 100):
+        A = torch.sparse_coo_tensor(idx[:, :cnt], v[:cnt], (n, m))
+        assert A._indices().data_ptr() == idx.data_ptr()
+        torch.testing.assert_close(sparse_mm(A, B), torch.sparse.mm(A, B), rtol=1e-5, atol=1e-6)
+    # CSR: col views of one buffer with different lengths
+    crow1 = torch.tensor([0, 2, 3], device=DEV, dtype=torch.int32)
+    crow2 = torch.tensor([0, 2, 4], device=DEV, dtype=torch.int32)
+    colbuf = torch.tensor([0, 2, 1, 3], device=DEV, dtype=torch.int32)
+    vals = torch.tensor([1.0, 2.0, 3.0, 4.0], device=DEV)
+    Bs = torch.rand(4, 4, device=DEV)
+    A1 = torch.sparse_csr_tensor(crow1, colbuf[:3], vals[:3], (2, 4))
+    A2 = torch.sparse_csr_tensor(crow2, colbuf[:4], vals[:4], (2, 4))
+    torch.testing.assert_close(sparse_mm(A1, Bs), A1.to_dense() @ Bs)
+    torch.testing.assert_close(sparse_mm(A2, Bs), A2.to_dense() @ Bs)
+    tsgu.clear_pattern_cache()
+
+
+def test_graphed_sparse_mm_survives_an_empty_pattern_cache():
+    """GraphedSparseMM pins its pattern: capture and replay work with the LRU cache switched off (capacity 0)."""
+    import torchsparsegradutils_b200 as tsgu
+    from torchsparsegradutils_b200 import GraphedSparseMM, sparse_mm
+
+    tsgu.set_pattern_cache_capacity(0)
+    try:
+        A = rand_csr(300, 200, 5, seed=11)
+        B = torch.rand(200, 16, device=DEV)
+        G = torch.rand(300, 16, device=DEV)
+        gs = GraphedSparseMM(A, B, G)
+        C, gAv, gB = gs(A.values(), B, G)
+        C2, gA2, gB2 = _run(A, B, G)
+        assert torch.equal(C, C2) and torch.equal(gAv, gA2.values()) and torch.equal(gB, gB2)
+    finally:
+        tsgu.set_pattern_cache_capacity(16)
+        tsgu.clear_pattern_cache()
+
+
+def test_pattern_cache_byte_cap_evicts():
+    import torchsparsegradutils_b200 as tsgu
+    from torchsparsegradutils_b200 import _pattern
+
+    tsgu.clear_pattern_cache()
+    old = _pattern._CACHE_BYTES
+    try:
+        mats = [rand_csr(2000, 2000, 8, seed=s) for s in range(4)]
+        one = _pattern.pattern_nbytes(_pattern.csr_pattern(mats[0]))
+        assert one >= 2000 * 8 * 4
+        tsgu.set_pattern_cache_capacity(16, max_bytes=int(2.5 * one))
+        for M in mats:
+            _pattern.csr_pattern(M)
+        assert 1 <= len(_pattern._cache) <= 2
+    finally:
+        tsgu.set_pattern_cache_capacity(16, max_bytes=old)
+        tsgu.clear_pattern_cache()
+
+
+def test_verify_mode_detects_rewritten_index_memory(monkeypatch):
+    """TSGU_B200_VERIFY_PATTERN=1 (debug mode): an in-place rewrite of index memory through an alias is caught."""
+    import torchsparsegradutils_b200 as tsgu
+    from torchsparsegradutils_b200 import _pattern, sparse_mm
+
+    tsgu.clear_pattern_cache()
+    monkeypatch.setattr(_pattern, "_VERIFY", True)
+    idx = torch.tensor([[0, 1], [0, 1]], device=DEV)
+    A = torch.sparse_coo_tensor(idx, torch.ones(2, device=DEV), (2, 2))
+    B = torch.tensor([[1.0, 2.0], [3.0, 4.0]], device=DEV)
+    assert torch.equal(sparse_mm(A, B), B)
+    idx[1] = torch.tensor([1, 0], device=DEV)  # alias write: no version bump on A._indices()
+    with pytest.raises(RuntimeError, match="rewritten in place"):
+        sparse_mm(A, B)
+    tsgu.clear_pattern_cache()
+    assert torch.equal(sparse_mm(A, B), B.flip(0))
+    tsgu.clear_pattern_cache()
+
+
+def test_unsupported_value_dtype_is_a_runtime_error():
+    from torchsparsegradutils_b200 import sparse_mm
+
+    A = rand_csr(8, 8, 2, seed=1)
+    Ah = torch.sparse_csr_tensor(A.crow_indices(), A.col_indices(), A.values().half(), A.shape)
+    with pytest.raises(RuntimeError, match="unsupported value dtype"):
+        sparse_mm(Ah, torch.rand(8, 4, device=DEV).half())

@@ -167,3 +167,24 @@ def test_stack_csr_matches_reference():
     assert torch.equal(st.crow_indices().cpu(), torch.from_numpy(GIDX["stack/crow"]))
     assert torch.equal(st.col_indices().cpu(), torch.from_numpy(GIDX["stack/col"]))
     assert torch.equal(st.to_dense().cpu(), torch.from_numpy(GIDX["stack/dense"]))
+
+
+def test_convert_preserves_int32_index_dtype_and_rejects_negatives():
+    """Reference utils/utils.py:228-231, :324: crow / col keep the dtype of the incoming coordinates; the permutation
+    is int64 (argsort).  Negative rows fail in the reference's _compress_row_indices check (:217)."""
+    import pytest
+    from torchsparsegradutils_b200.utils.utils import _sort_coo_indices, convert_coo_to_csr_indices_values
+
+    idx = torch.tensor([[2, 0, 1, 0], [1, 3, 0, 0]], dtype=torch.int32, device="cuda:0")
+    crow, col, perm = convert_coo_to_csr_indices_values(idx, 3)
+    assert crow.dtype == torch.int32 and col.dtype == torch.int32 and perm.dtype == torch.int64
+    assert crow.tolist() == [0, 2, 3, 4] and col.tolist() == [0, 3, 0, 1] and perm.tolist() == [3, 1, 2, 0]
+    srt, p = _sort_coo_indices(idx)
+    assert srt.dtype == torch.int32 and p.dtype == torch.int64
+    # values of a dtype / shape the native gather does not cover go through index_select like the reference's values[perm]
+    hv = torch.arange(8, device="cuda:0", dtype=torch.float16).reshape(4, 2)
+    _, _, v = convert_coo_to_csr_indices_values(idx, 3, hv)
+    assert torch.equal(v, hv[perm])
+    bad = torch.tensor([[0, -1], [0, 1]], device="cuda:0")
+    with pytest.raises(ValueError, match="negative"):
+        convert_coo_to_csr_indices_values(bad, 3)

@@ -77,9 +77,17 @@ class _timed:
             self.kt.records.append((self.tag, self.e0, self.e1))
 
 
+def _epv(dtype: torch.dtype) -> int:
+    try:
+        return _VEC_ELEMS[dtype]
+    except KeyError:
+        nat.val_enum(dtype)  # raises the documented RuntimeError for unsupported dtypes
+        raise
+
+
 def _vector_ready(x: torch.Tensor) -> bool:
     """Can the 128-bit kernels read this (batch, rows, K) operand in place?"""
-    epv = _VEC_ELEMS[x.dtype]
+    epv = _epv(x.dtype)
     bs, rs, cs = x.stride()
     K = x.shape[-1]
     if K % epv:
@@ -130,7 +138,7 @@ def prepare_dense(x: torch.Tensor) -> torch.Tensor:
     view, which is what ``_batch_sparse_mv`` hands us, distributions/sparse_multivariate_normal.py:96,100).
     Other K: the scalar kernels take arbitrary element strides, no copy.
     """
-    if x.shape[-1] % _VEC_ELEMS[x.dtype] == 0 and not _vector_ready(x):
+    if x.shape[-1] % _epv(x.dtype) == 0 and not _vector_ready(x):
         return pack_dense(x)
     return x
 

@@ -7,15 +7,24 @@ inputs (``utils/utils.py:474-645``), a ``repeat_interleave`` row expansion in ev
 (``tests/test_sparse_matmul.py:295-338``), so here every derived structure (COO->CSR order, the
 transpose) is built once per pattern by the index-builder kernels and cached.
 
-A cache entry keeps a reference to the index tensors it was built from, so their storage cannot be
-recycled for a different pattern while the entry lives, and it is invalidated by an in-place edit
-(``Tensor._version``).  Entries are evicted LRU; ``clear_pattern_cache()`` drops everything.
+Cache contract.  An entry is keyed on the *identity of the index memory*: data pointer, element count,
+shape, strides, storage offset, dtype and version counter of every index tensor, plus the sparse shape.  It
+keeps a reference to those tensors, so their storage cannot be recycled for a different pattern while the
+entry lives.  What the key cannot see is an in-place write through an *unrelated alias* of the same storage
+(``idx.copy_(new)`` on the buffer a sparse tensor was built from: torch gives ``_indices()`` /
+``crow_indices()`` their own version counters): while a pattern is cached its index memory is **frozen**;
+call ``clear_pattern_cache()`` after rewriting index buffers in place, or run with
+``TSGU_B200_VERIFY_PATTERN=1``, which re-checksums the index arrays on every hit (one host sync per call; a
+debug mode).  Entries are evicted LRU under both an entry cap and a byte cap (``set_pattern_cache_capacity``,
+``TSGU_B200_PATTERN_CACHE_BYTES``); ``clear_pattern_cache()`` drops everything.  Objects that must not lose
+their pattern to eviction (``GraphedSparseMM``) pin it with :func:`pin_pattern`.
 """
 from __future__ import annotations
 
 import ctypes
 import os
 import threading
+import weakref
 from collections import OrderedDict
 from dataclasses import dataclass, field
 from typing import Optional
@@ -25,7 +34,10 @@ import torch
 from . import _native as nat
 
 _CACHE_CAPACITY = 16
+_CACHE_BYTES = int(os.environ.get("TSGU_B200_PATTERN_CACHE_BYTES", str(8 << 30)))  # derived structures + kept index tensors
+_VERIFY = os.environ.get("TSGU_B200_VERIFY_PATTERN", "0") == "1"
 _cache: "OrderedDict[tuple, object]" = OrderedDict()
+_pinned: "weakref.WeakValueDictionary[tuple, object]" = weakref.WeakValueDictionary()
 _cache_lock = threading.Lock()
 _I32_MAX = 2**31 - 1
 
@@ -33,14 +45,71 @@ _I32_MAX = 2**31 - 1
 def clear_pattern_cache() -> None:
     with _cache_lock:
         _cache.clear()
+        _pinned.clear()
 
 
-def set_pattern_cache_capacity(n: int) -> None:
-    global _CACHE_CAPACITY
+def set_pattern_cache_capacity(n: int, max_bytes: Optional[int] = None) -> None:
+    """Cap the cache at `n` patterns and (optionally) `max_bytes` of device memory held by them."""
+    global _CACHE_CAPACITY, _CACHE_BYTES
     _CACHE_CAPACITY = max(int(n), 0)
+    if max_bytes is not None:
+        _CACHE_BYTES = max(int(max_bytes), 0)
     with _cache_lock:
-        while len(_cache) > _CACHE_CAPACITY:
-            _cache.popitem(last=False)
+        _evict_locked()
+
+
+def _index_key(t: torch.Tensor) -> tuple:
+    """Identity of an index tensor's memory (not of its contents -- see the module docstring)."""
+    return (t.data_ptr(), t.numel(), tuple(t.shape), tuple(t.stride()), t.storage_offset(), t.dtype, t._version)
+
+
+def _tensor_bytes(t) -> int:
+    return t.numel() * t.element_size() if isinstance(t, torch.Tensor) else 0
+
+
+def pattern_nbytes(p) -> int:
+    """Device bytes a cached pattern keeps alive (index tensors it was built from included)."""
+    if p is None:
+        return 0
+    if isinstance(p, CooPattern):
+        return (pattern_nbytes(p.csr) + sum(_tensor_bytes(t) for t in (p.grad_indices, p.seg, p.sort_perm))
+                + (_tensor_bytes(p.out_index) if p.out_index is not p.csr.perm else 0))
+    total = sum(_tensor_bytes(t) for t in (p.rowptr, p.colind, p.perm))
+    total += sum(_tensor_bytes(t) for t in p.keep if isinstance(t, torch.Tensor) and t is not p.rowptr and t is not p.colind)
+    if p.split is not None:
+        total += sum(_tensor_bytes(t) for t in (p.split.vrowptr, p.split.row_map, p.split.g_map, p.split.cut_rows, p.split.cut_ptr))
+    for extra in p.extras.values():
+        total += sum(_tensor_bytes(t) for t in (extra if isinstance(extra, (tuple, list)) else (extra,)))
+    return total + pattern_nbytes(p._transpose)
+
+
+def _evict_locked() -> None:
+    while len(_cache) > _CACHE_CAPACITY:
+        _cache.popitem(last=False)
+    if len(_cache) > 1:  # the byte cap never evicts the most recent entry (it is the one in use)
+        sizes = {k: pattern_nbytes(v) for k, v in _cache.items()}
+        total = sum(sizes.values())
+        while total > _CACHE_BYTES and len(_cache) > 1:
+            k, _ = _cache.popitem(last=False)
+            total -= sizes[k]
+
+
+def _fingerprint(*tensors: torch.Tensor) -> torch.Tensor:
+    """Position-weighted checksum of index arrays (device scalar); TSGU_B200_VERIFY_PATTERN only."""
+    acc = None
+    for t in tensors:
+        f = t.reshape(-1).to(torch.int64)
+        w = (torch.arange(f.numel(), device=f.device, dtype=torch.int64) % 65521) + 1
+        c = (f * w).sum() + f.numel()
+        acc = c if acc is None else acc * 1000003 + c
+    return acc
+
+
+def pin_pattern(key, pattern) -> None:
+    """Keep `pattern` reachable under `key` for as long as the caller holds a reference to it, whatever the LRU
+    does (weak registry: the entry dies with its owner)."""
+    with _cache_lock:
+        _pinned[key] = pattern
 
 
 @dataclass
@@ -60,6 +129,9 @@ class CsrPattern:
     algo: int = nat.ALGO_AUTO  # kernel family chosen once per pattern from its row-length skew
     split: Optional["SplitRows"] = None  # virtual-row view of a skewed pattern (algo == ALGO_SPLIT)
     keep: tuple = ()  # tensors whose storage must outlive this pattern (cache-key owners)
+    extras: dict = field(default_factory=dict, repr=False)  # per-pattern plans built lazily by _ops (window plans, ...)
+    fingerprint: Optional[torch.Tensor] = field(default=None, repr=False)
+    cache_key: Optional[tuple] = field(default=None, repr=False)
     _transpose: Optional["CsrPattern"] = field(default=None, repr=False)
     _uniform: Optional[bool] = field(default=None, repr=False)
     _lock: threading.Lock = field(default_factory=threading.Lock, repr=False)
@@ -223,30 +295,38 @@ def _pad_rows(rowptr: torch.Tensor, colind: torch.Tensor, perm: torch.Tensor, mu
     return new_rowptr.to(rowptr.dtype), colind_p, perm_p, total
 
 
-def _cache_get(key):
+def _cache_get(key, index_tensors=()):
     with _cache_lock:
         hit = _cache.get(key)
         if hit is not None:
             _cache.move_to_end(key)
-        return hit
+        else:
+            hit = _pinned.get(key)
+    if hit is not None and _VERIFY:
+        fp = getattr(hit, "fingerprint", None)
+        if fp is not None and not bool(fp == _fingerprint(*index_tensors)):
+            raise RuntimeError(
+                "torchsparsegradutils_b200: the index memory of a cached sparsity pattern was rewritten in place "
+                "(pattern memory is frozen while cached); call clear_pattern_cache() after editing index buffers")
+    return hit
 
 
-def _cache_put(key, value):
+def _cache_put(key, value, index_tensors=()):
+    if _VERIFY:
+        value.fingerprint = _fingerprint(*index_tensors)
     if _CACHE_CAPACITY == 0:
         return
     with _cache_lock:
         _cache[key] = value
-        while len(_cache) > _CACHE_CAPACITY:
-            _cache.popitem(last=False)
+        _evict_locked()
 
 
 # ------------------------------------------------------------------------------------------ CSR
 def csr_pattern(A: torch.Tensor) -> CsrPattern:
     """Pattern of a (batched) torch CSR tensor: a zero-copy view of its crow/col arrays."""
     crow, col = A.crow_indices(), A.col_indices()
-    key = ("csr", crow.data_ptr(), col.data_ptr(), crow._version, col._version, tuple(A.shape), crow.dtype,
-           crow.device)
-    hit = _cache_get(key)
+    key = ("csr", _index_key(crow), _index_key(col), tuple(A.shape), crow.device)
+    hit = _cache_get(key, (crow, col))
     if hit is not None:
         return hit
     batched = A.dim() == 3
@@ -257,7 +337,8 @@ def csr_pattern(A: torch.Tensor) -> CsrPattern:
     pat = _with_split(CsrPattern(crow_c, col_c, None, batch, n, m, n + 1, nnz_item, batch * nnz_item,
                                  nat.idx_enum(crow.dtype), algo=choose_algo(crow_c, batch, n, batch * nnz_item),
                                  keep=(crow, col)))
-    _cache_put(key, pat)
+    pat.cache_key = key
+    _cache_put(key, pat, (crow, col))
     return pat
 
 
@@ -274,6 +355,8 @@ class CooPattern:
     seg: Optional[torch.Tensor]  # (nnz_unique + 1) run offsets into the sorted order when duplicates exist
     sort_perm: Optional[torch.Tensor]  # sorted position -> storage position (for segment sums)
     nnz_unique: int
+    fingerprint: Optional[torch.Tensor] = field(default=None, repr=False)
+    cache_key: Optional[tuple] = field(default=None, repr=False)
 
 
 def _sort_coo(indices: torch.Tensor, dims, key_dims: int, perm_idx: int, want_sorted: bool):
@@ -313,10 +396,11 @@ def coo_pattern(A: torch.Tensor) -> CooPattern:
     """COO -> kernel-ready structure (sort + rowptr), cached per index tensor."""
     ind = A._indices()
     coalesced = A.is_coalesced()
-    key = ("coo", ind.data_ptr(), ind._version, tuple(A.shape), coalesced, ind.device)
-    hit = _cache_get(key)
+    key = ("coo", _index_key(ind), tuple(A.shape), coalesced, ind.device)
+    hit = _cache_get(key, (ind,))
     if hit is not None:
         return hit
+    ind_key = ind
     if ind.stride(1) != 1:
         ind = ind.contiguous()
     batched = A.dim() == 3
@@ -355,5 +439,6 @@ def coo_pattern(A: torch.Tensor) -> CooPattern:
                 seg = torch.cat([starts, starts.new_tensor([nnz])]).to(nat.IDX_TORCH[idx])
                 csr = _coo_to_flat_csr(uniq, batch, n, m, None, idx, keep=(ind,))
                 pat = CooPattern(csr, None, uniq, seg, perm, uniq.shape[1])
-    _cache_put(key, pat)
+    pat.cache_key = key
+    _cache_put(key, pat, (ind_key,))
     return pat

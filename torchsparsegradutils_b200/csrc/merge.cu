@@ -29,14 +29,6 @@
 #ifndef TSGU_MERGE_LOADS
 #define TSGU_MERGE_LOADS 16  // 128-bit dense-row loads in flight per lane (SpMM)
 #endif
-#ifndef TSGU_MERGE_HEAD_IN_REGS
-#define TSGU_MERGE_HEAD_IN_REGS 0  // 1: a group's head partial stays in its own registers (it is only ever read back by the
-                                   // same lanes), halving the partial buffers in shared memory -> room for larger tiles
-                                   // (experiment, not yet measured; sweep with TSGU_MERGE_P=4096)
-#endif
-#ifndef TSGU_MERGE_SDDMM_PREFETCH
-#define TSGU_MERGE_SDDMM_PREFETCH 0  // 1: prefetch the next row of G in the merge-path SDDMM (experiment, see the kernel)
-#endif
 #ifndef TSGU_MERGE_SDDMM_LOADS
 #define TSGU_MERGE_SDDMM_LOADS 8  // ... and in the SDDMM, which wants more warps instead (row changes stall on a G-row fetch)
 #endif
@@ -121,13 +113,9 @@ struct MergeSpmmSmem {
   static constexpr int GROUPS = 256 / LPR;
   static constexpr int KSLOT = LPR * VPL * (16 / (int)sizeof(V));  // accumulators per partial vector (>= K)
   MergeStage<V, I, VALS> st[2];
-#if !TSGU_MERGE_HEAD_IN_REGS
   alignas(16) Acc head[GROUPS][KSLOT];
-#endif
   alignas(16) Acc tail[GROUPS][KSLOT];
-#if !TSGU_MERGE_HEAD_IN_REGS
   int64_t head_row[GROUPS];
-#endif
   int64_t tail_row[GROUPS];
   alignas(8) uint64_t full[2];
 };
@@ -226,16 +214,7 @@ __global__ void __launch_bounds__(256, TSGU_MERGE_MINB) spmm_merge_kernel(const 
     int rowl = gi0l;
     int row_end = rowl < gi1l ? (int)((int64_t)rp[rowl + 1] - tj0) : INT_MAX;
     bool head = gi0 < p.rows && (int64_t)rp[gi0l] < gj0;  // the first row began before this group's range
-#if TSGU_MERGE_HEAD_IN_REGS
-    Acc hacc[VPL][EPV];
-    int64_t my_head_row = -1;
-#pragma unroll
-    for (int w = 0; w < VPL; ++w)
-#pragma unroll
-      for (int i = 0; i < EPV; ++i) hacc[w][i] = Acc(0);
-#else
     if (gl == 0) sm.head_row[group] = -1;
-#endif
     if (tid == 0) p.carry_row[t * 2 + 0] = -1;  // overwritten after the barrier if this tile has a head partial
 
     // finish the current row: interior rows go straight to C, a head row that began before this group's
@@ -245,13 +224,8 @@ __global__ void __launch_bounds__(256, TSGU_MERGE_MINB) spmm_merge_kernel(const 
 #pragma unroll
         for (int w = 0; w < VPL; ++w)
 #pragma unroll
-#if TSGU_MERGE_HEAD_IN_REGS
-          for (int i = 0; i < EPV; ++i) hacc[w][i] = acc[w][i];
-        my_head_row = gi0;
-#else
           for (int i = 0; i < EPV; ++i) sm.head[group][(w * LPR + gl) * EPV + i] = acc[w][i];
         if (gl == 0) sm.head_row[group] = gi0;
-#endif
         head = false;
       } else {
         V* Crow = p.C + (ti0 + rowl) * p.ldc;
@@ -347,11 +321,7 @@ __global__ void __launch_bounds__(256, TSGU_MERGE_MINB) spmm_merge_kernel(const 
 
     // ---- ordered combine of rows cut by group boundaries --------------------------------
     {
-#if TSGU_MERGE_HEAD_IN_REGS
-      const int64_t hr = my_head_row;
-#else
       const int64_t hr = sm.head_row[group];
-#endif
       if (hr >= 0) {
         int glo = group;
         while (glo > 0 && sm.tail_row[glo - 1] == hr) --glo;
@@ -368,11 +338,7 @@ __global__ void __launch_bounds__(256, TSGU_MERGE_MINB) spmm_merge_kernel(const 
 #pragma unroll
         for (int w = 0; w < VPL; ++w)
 #pragma unroll
-#if TSGU_MERGE_HEAD_IN_REGS
-          for (int i = 0; i < EPV; ++i) tot[w][i] += hacc[w][i];
-#else
           for (int i = 0; i < EPV; ++i) tot[w][i] += sm.head[group][(w * LPR + gl) * EPV + i];
-#endif
         const bool from_earlier_tile = (glo == 0) && ((int64_t)rp[(int)(hr - ti0)] < tj0);
         if (from_earlier_tile) {  // completed by the fix-up kernel together with earlier tiles' tails
           Acc* dst = p.carry + (t * 2 + 0) * p.kpad;
@@ -672,32 +638,6 @@ __global__ void __launch_bounds__(256, TSGU_MERGE_SDDMM_MINB) sddmm_merge_kernel
         }
       };
       load_g();
-#if TSGU_MERGE_SDDMM_PREFETCH
-      // Experiment (off by default, not yet measured): keep the raw G row of the NEXT row that owns entries in
-      // flight while the current row is consumed, so a row change costs an unpack instead of a global-load stall.
-      Raw<V, EPV> gn[VPL];
-      int nrow = rowl;
-      const int rows_last = (int)(ti1 - ti0);  // last local row that can own entries of this tile
-      auto prefetch = [&]() {
-        int q = rowl + 1;
-        while (q <= rows_last && ti0 + q < p.rows && (int64_t)rp[q + 1] == (int64_t)rp[q]) ++q;  // empty rows
-        nrow = q;
-        const bool valid = q <= rows_last && ti0 + q < p.rows;
-        const V* Grow = p.G + (ti0 + (valid ? q : rowl)) * p.g_rs;
-#pragma unroll
-        for (int w = 0; w < VPL; ++w)
-          gn[w] = (EXACT || on[w]) ? raw_ldg<V, EPV>(Grow + (int64_t)(w * LPR + gl) * EPV) : raw_zero<V, EPV>();
-      };
-      prefetch();
-      auto next_row = [&](int eu) {  // entries are consecutive, so the row that owns `eu` is the prefetched one
-        (void)eu;
-        rowl = nrow;
-        row_end = local_end(rowl);
-#pragma unroll
-        for (int w = 0; w < VPL; ++w) raw_unpack<V, EPV>(gn[w], g[w]);
-        prefetch();
-      };
-#else
       auto next_row = [&](int eu) {  // skip empties, fetch that row of G
         do {
           ++rowl;
@@ -705,7 +645,6 @@ __global__ void __launch_bounds__(256, TSGU_MERGE_SDDMM_MINB) sddmm_merge_kernel
         } while (eu >= row_end);
         load_g();
       };
-#endif
       auto dot = [&](const uint4 (&bu)[VPL], Acc& out) {
 #pragma unroll
         for (int w = 0; w < VPL; ++w) {

@@ -11,6 +11,7 @@ from typing import Tuple
 
 import torch
 
+from ._pattern import coo_pattern, csr_pattern, pin_pattern
 from .sparse_matmul import sparse_mm
 
 
@@ -47,7 +48,12 @@ class GraphedSparseMM:
 
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):  # warm the pattern cache (sort / transpose builds are not capturable)
+        with torch.cuda.stream(side):
+            # The pattern builds (sort / transpose, with their host syncs) are not capturable: build the pattern
+            # here and PIN it to this object, so the capture below -- and nothing later -- depends on what the
+            # LRU pattern cache happens to hold (it may have capacity 0, or evict the entry between steps).
+            self._pattern = csr_pattern(self._A) if self._csr else coo_pattern(self._A)
+            pin_pattern(self._pattern.cache_key, self._pattern)
             for _ in range(max(warmup, 1)):
                 step()
         torch.cuda.current_stream(dev).wait_stream(side)

@@ -19,12 +19,11 @@ grad_B = A^T G          torch.sparse.mm(A.t(), G) (``:229``)             cached 
 """
 from __future__ import annotations
 
-import os
 from typing import cast
 
 import torch
 
-from . import _ops
+from . import _native, _ops
 from ._pattern import CooPattern, CsrPattern, coo_pattern, csr_pattern
 
 
@@ -80,6 +79,7 @@ def _check_runtime(A: torch.Tensor, B: torch.Tensor) -> None:
         raise RuntimeError(f"sparse_mm: A and B must be on the same device, got {A.device} and {B.device}")
     if A.dtype != B.dtype:
         raise RuntimeError(f"sparse_mm: A and B must have the same dtype, got {A.dtype} and {B.dtype}")
+    _native.val_enum(B.dtype)  # RuntimeError("unsupported value dtype ...") for float16 / complex / integer operands
     if A.layout == torch.sparse_coo and (A.sparse_dim() != A.dim() or A.dense_dim() != 0):
         raise RuntimeError("sparse_mm: COO input must have sparse_dim == ndim and no dense dimensions")
 
@@ -120,46 +120,9 @@ class SparseMatMul(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad):  # type: ignore[override]
-        if _OVERLAP_GATHER and ctx.needs_input_grad[0] and ctx.needs_input_grad[1]:
-            return _backward_overlapped(ctx, grad)
         gradA = _grad_A(ctx, grad) if ctx.needs_input_grad[0] else None
         gradB = _grad_B(ctx, grad) if ctx.needs_input_grad[1] else None
         return gradA, gradB
-
-
-# Experiment (off by default, not yet measured): the transposed pass first gathers A's values into
-# transposed order (0.05 ms on config 2, 0.28 ms on config 3).  That pass depends only on A, so it can run on a side
-# stream while the SDDMM (grad_A) occupies the main one.  TSGU_B200_OVERLAP_GATHER=1 turns it on.
-_OVERLAP_GATHER = os.environ.get("TSGU_B200_OVERLAP_GATHER", "0") == "1"
-_side_streams: dict = {}
-
-
-def _backward_overlapped(ctx, grad):
-    saved = ctx.saved_tensors
-    A = saved[0]
-    pat = ctx.pattern
-    is_csr = isinstance(pat, CsrPattern)
-    csr = pat if is_csr else cast(CooPattern, pat).csr
-    patT = csr.transpose()
-    if not _ops.wants_pregather(patT):
-        return _grad_A(ctx, grad), _grad_B(ctx, grad)
-    vals = saved[2] if len(saved) > 2 else (A.values() if is_csr else A._values()).contiguous()
-    dev = grad.device
-    main = torch.cuda.current_stream(dev)
-    side = _side_streams.get(dev.index)
-    if side is None:
-        side = _side_streams[dev.index] = torch.cuda.Stream(dev)
-    side.wait_stream(main)  # vals (and, under graph capture, the fork) are ordered after what main has done so far
-    with torch.cuda.stream(side):
-        vals_T = _ops.gather_values(vals.reshape(-1), patT.perm)
-    gradA = _grad_A(ctx, grad)  # SDDMM on the main stream, concurrent with the gather
-    main.wait_stream(side)
-    vals_T.record_stream(main)
-    gradB = _ops.spmm(patT, vals_T, grad, tag="spmm_gradB", vals_in_pattern_order=True)
-    gradB = gradB if ctx.batched else gradB[0]
-    if ctx.B_strides is not None:
-        gradB = _ops.restride_like(gradB, ctx.B_shape, ctx.B_strides)
-    return gradA, gradB
 
 
 def _grad_A(ctx, grad):
