@@ -204,6 +204,36 @@ TSGU_API int tsgu_pack_dense(const void* src, void* dst, int64_t batch, int64_t 
                     int64_t s_bs, int64_t s_rs, int64_t s_cs, int64_t d_bs, int64_t d_rs, int64_t d_cs,
                     int val_dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Column-window kernels for structured (banded / stencil) patterns -- same products as
+ * tsgu_spmm_csr / tsgu_sddmm_csr (sparse_matmul.py:155, :229, :190-205), for patterns
+ * whose tiles of consecutive rows touch few contiguous runs of columns (the 27-point
+ * PairwiseEncoder matrices of encoders/pairwise_encoder.py:383-505).
+ *
+ * tsgu_window_plan (once per pattern): for tiles of `tile_rows` rows writes
+ *   lcol  uint16 per stored entry (same indexing as colind): slot of the entry's column in
+ *         its tile's window (the dense rank of the column among the tile's distinct columns)
+ *   desc  32 int32 per tile: [0] number of column runs (-1: tile does not fit the limits of
+ *         tsgu_window_limits), [1] distinct columns, then per run {first column, slot | len << 16}
+ *   stats int32[4]: tiles that do not fit, max distinct columns, max runs, max entries per tile
+ * The plan is usable iff stats[0] == 0.  32-bit index structures only (idx_dtype == TSGU_I32
+ * for the compute entry points).  The compute kernels need K * sizeof(value) in {64, 128, 256}
+ * bytes and 16-byte aligned dense rows; C / out are written exactly like the _csr entry points. */
+TSGU_API int tsgu_window_limits(int* tile_rows_max, int* entries_max, int* window_rows, int* runs_max);
+TSGU_API int tsgu_window_plan(const void* rowptr, const void* colind, int64_t batch, int64_t n,
+                     int64_t rowptr_bstride, int64_t nnz_bstride, int idx_dtype, int tile_rows,
+                     void* lcol_out, void* desc_out, void* stats_out, void* stream);
+TSGU_API int tsgu_spmm_window(const void* rowptr, const void* lcol, const void* desc, const void* vals,
+                     const void* perm, const void* B, void* C, int64_t batch, int64_t n, int64_t K,
+                     int64_t rowptr_bstride, int64_t nnz_bstride, int64_t nnz_len, int tile_rows,
+                     int64_t b_bs, int64_t b_rs, int64_t c_bs, int64_t ldc, int val_dtype, int idx_dtype,
+                     void* stream);
+TSGU_API int tsgu_sddmm_window(const void* rowptr, const void* lcol, const void* desc, const void* out_index,
+                      const void* G, const void* B, void* out, int64_t batch, int64_t n, int64_t K,
+                      int64_t rowptr_bstride, int64_t nnz_bstride, int64_t nnz_len, int tile_rows,
+                      int64_t g_bs, int64_t g_rs, int64_t b_bs, int64_t b_rs, int val_dtype, int idx_dtype,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

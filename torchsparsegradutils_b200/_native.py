@@ -51,6 +51,10 @@ _SIGNATURES = {
     "tsgu_gather_values": (_I, [_P, _P, _P, _L, _I, _I, _P]),
     "tsgu_segment_sum_values": (_I, [_P, _P, _P, _P, _L, _I, _I, _P]),
     "tsgu_pack_dense": (_I, [_P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _P]),
+    "tsgu_window_limits": (_I, [_P, _P, _P, _P]),
+    "tsgu_window_plan": (_I, [_P, _P, _L, _L, _L, _L, _I, _I, _P, _P, _P, _P]),
+    "tsgu_spmm_window": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _I, _L, _L, _L, _L, _I, _I, _P]),
+    "tsgu_sddmm_window": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _I, _L, _L, _L, _L, _I, _I, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

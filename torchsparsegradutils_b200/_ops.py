@@ -1,12 +1,13 @@
 """Thin launchers: torch tensors in, C-ABI calls on the current stream, torch tensors out."""
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
 
 from . import _native as nat
-from ._pattern import CsrPattern
+from ._pattern import CsrPattern, WindowPlan, window_plan
 
 _VEC_ELEMS = {torch.float32: 4, torch.float64: 2, torch.bfloat16: 8}
 _PREGATHER_MIN_NNZ = 1 << 18
@@ -178,6 +179,42 @@ def wants_pregather(pat: CsrPattern) -> bool:
     return pat.perm is not None and pat.nnz_total >= _PREGATHER_MIN_NNZ and pat.algo != nat.ALGO_SPLIT
 
 
+_WINDOW_ROW_BYTES = (64, 128, 256)  # dense row widths the column-window kernels are built for (csrc/window.cu)
+_WINDOW_PERM_IN_KERNEL = os.environ.get("TSGU_B200_WINDOW_PERM", "0") == "1"
+
+
+def _window_for(pat: CsrPattern, algo: int, *dense: torch.Tensor) -> Optional[WindowPlan]:
+    """The pattern's column-window plan if the window kernels can take these operands, else None."""
+    if algo != nat.ALGO_AUTO:
+        return None
+    d0 = dense[0]
+    if d0.dtype not in (torch.float32, torch.bfloat16) or d0.shape[-1] * d0.element_size() not in _WINDOW_ROW_BYTES:
+        return None
+    if not all(_vector_ready(x) for x in dense):
+        return None
+    return window_plan(pat)
+
+
+def _spmm_window(pat: CsrPattern, wp: WindowPlan, vals: torch.Tensor, dense: torch.Tensor, tag: str,
+                 vals_in_pattern_order: bool) -> torch.Tensor:
+    dev = dense.device
+    K = dense.shape[-1]
+    out = torch.empty((pat.batch, pat.n, K), dtype=dense.dtype, device=dev)
+    perm = None if vals_in_pattern_order else pat.perm
+    if perm is not None and not _WINDOW_PERM_IN_KERNEL:
+        with _timer(tag + "_gather", dev):
+            vals = gather_values(vals.reshape(-1), perm)
+        perm = None
+    bs, rs, _ = _strides(dense)
+    with _on(dev), _timer(tag, dev):
+        nat.check(nat.lib().tsgu_spmm_window(nat.ptr(pat.rowptr), nat.ptr(wp.lcol), nat.ptr(wp.desc), nat.ptr(vals),
+                                             nat.ptr(perm), dense.data_ptr(), out.data_ptr(), pat.batch, pat.n, K,
+                                             pat.rowptr_bstride, pat.nnz_bstride, pat.colind.numel(), wp.tile_rows,
+                                             bs, rs if pat.m > 1 else K, pat.n * K, K, nat.val_enum(dense.dtype), pat.idx,
+                                             nat.stream_ptr(dev)), "tsgu_spmm_window")
+    return out
+
+
 def spmm(pat: CsrPattern, vals: torch.Tensor, dense: torch.Tensor, algo: Optional[int] = None,
          tag: str = "spmm", vals_in_pattern_order: bool = False) -> torch.Tensor:
     """out[t] = A[t] @ dense[t]; dense is (batch, m, K) (any strides); returns contiguous (batch, n, K).
@@ -190,6 +227,10 @@ def spmm(pat: CsrPattern, vals: torch.Tensor, dense: torch.Tensor, algo: Optiona
         algo = nat.ALGO_MERGE  # scalar / oversized K: the merge-path (or row-split) kernels take it
     dense = prepare_dense(_as3d(dense))
     K = dense.shape[-1]
+    if pat.batch * pat.n * K and pat.nnz_total:
+        wp = _window_for(pat, algo, dense)
+        if wp is not None:
+            return _spmm_window(pat, wp, vals, dense, tag, vals_in_pattern_order)
     out = torch.empty((pat.batch, pat.n, K), dtype=dense.dtype, device=dense.device)
     if out.numel() == 0:
         return out
@@ -269,6 +310,18 @@ def sddmm(pat: CsrPattern, G: torch.Tensor, B: torch.Tensor, out_index: Optional
         return out
     dev = B.device
     L = nat.lib()
+    wp = _window_for(pat, algo, B, G) if pat.nnz_total else None
+    if wp is not None:
+        K = B.shape[-1]
+        gbs, grs, _ = _strides(G)
+        bbs, brs, _ = _strides(B)
+        with _on(dev), _timer("sddmm", dev):
+            nat.check(L.tsgu_sddmm_window(nat.ptr(pat.rowptr), nat.ptr(wp.lcol), nat.ptr(wp.desc), nat.ptr(out_index),
+                                          G.data_ptr(), B.data_ptr(), out.data_ptr(), pat.batch, pat.n, K,
+                                          pat.rowptr_bstride, pat.nnz_bstride, pat.colind.numel(), wp.tile_rows,
+                                          gbs, grs if pat.n > 1 else K, bbs, brs if pat.m > 1 else K,
+                                          nat.val_enum(B.dtype), pat.idx, nat.stream_ptr(dev)), "tsgu_sddmm_window")
+        return out
     with _on(dev), _timer("sddmm", dev):
         ws_bytes = L.tsgu_sddmm_workspace_bytes(pat.batch, pat.n, pat.nnz_total, algo) if algo == nat.ALGO_MERGE else 0
         ws = nat.workspace(ws_bytes, dev) if ws_bytes else None

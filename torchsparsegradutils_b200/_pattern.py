@@ -79,6 +79,8 @@ def pattern_nbytes(p) -> int:
     if p.split is not None:
         total += sum(_tensor_bytes(t) for t in (p.split.vrowptr, p.split.row_map, p.split.g_map, p.split.cut_rows, p.split.cut_ptr))
     for extra in p.extras.values():
+        if isinstance(extra, WindowPlan):
+            extra = (extra.lcol, extra.desc)
         total += sum(_tensor_bytes(t) for t in (extra if isinstance(extra, (tuple, list)) else (extra,)))
     return total + pattern_nbytes(p._transpose)
 
@@ -230,6 +232,65 @@ def _internal_idx(batch: int, rows: int, cols: int, nnz: int) -> int:
     return nat.I32 if max(batch * rows + 1, batch * cols + 1, nnz) < _I32_MAX else nat.I64
 
 
+# ------------------------------------------------------------------------------ column-window plans
+@dataclass
+class WindowPlan:
+    """Per-pattern plan of the column-window kernels (csrc/window.cu): a 16-bit window slot per stored entry and a
+    run descriptor per tile of `tile_rows` rows."""
+
+    lcol: torch.Tensor   # int16 storage of the uint16 slots, same indexing as colind
+    desc: torch.Tensor   # int32 (num_tiles, 32)
+    tile_rows: int
+    max_window_rows: int
+    max_runs: int
+    max_entries: int
+
+
+_WINDOW_ON = os.environ.get("TSGU_B200_WINDOW", "1") != "0"
+_WINDOW_MIN_NNZ = int(os.environ.get("TSGU_B200_WINDOW_MIN_NNZ", str(1 << 18)))
+_WINDOW_MIN_ROWS = int(os.environ.get("TSGU_B200_WINDOW_MIN_ROWS", str(64 * 2 * 148)))
+_window_limits = None
+
+
+def window_limits():
+    global _window_limits
+    if _window_limits is None:
+        v = [ctypes.c_int(0) for _ in range(4)]
+        nat.check(nat.lib().tsgu_window_limits(*[ctypes.byref(x) for x in v]), "tsgu_window_limits")
+        _window_limits = dict(tile_rows=v[0].value, entries=v[1].value, window_rows=v[2].value, runs=v[3].value)
+    return _window_limits
+
+
+def window_plan(p: "CsrPattern") -> Optional[WindowPlan]:
+    """Column-window plan of a pattern, or None when the pattern is not structured enough (some tile of consecutive
+    rows touches more distinct columns / runs than a shared-memory window holds).  Built once per pattern by
+    tsgu_window_plan (one kernel, one host sync for the verdict) and cached with it."""
+    if "window" in p.extras:
+        return p.extras["window"]
+    plan = None
+    rows = p.batch * p.n
+    if (_WINDOW_ON and p.idx == nat.I32 and p.algo == nat.ALGO_AUTO and p.nnz_total >= _WINDOW_MIN_NNZ
+            and rows >= _WINDOW_MIN_ROWS and p.m < _I32_MAX):
+        lim = window_limits()
+        avg = p.nnz_total / rows
+        tile_rows = next((t for t in (32, 16, 8) if t <= lim["tile_rows"] and t * avg <= lim["entries"]), 0)
+        if tile_rows:
+            dev = p.device
+            tiles = p.batch * (-(-p.n // tile_rows))
+            lcol = torch.empty(p.colind.numel(), dtype=torch.int16, device=dev)
+            desc = torch.empty((tiles, 32), dtype=torch.int32, device=dev)
+            stats = torch.empty(4, dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                nat.check(nat.lib().tsgu_window_plan(nat.ptr(p.rowptr), nat.ptr(p.colind), p.batch, p.n, p.rowptr_bstride,
+                                                     p.nnz_bstride, p.idx, tile_rows, nat.ptr(lcol), nat.ptr(desc),
+                                                     nat.ptr(stats), nat.stream_ptr(dev)), "tsgu_window_plan")
+            failed, max_w, max_runs, max_entries = stats.tolist()  # the one host sync of the plan
+            if failed == 0:
+                plan = WindowPlan(lcol, desc, tile_rows, max_w, max_runs, max_entries)
+    p.extras["window"] = plan
+    return plan
+
+
 def _build_transpose(p: CsrPattern) -> CsrPattern:
     dev = p.device
     out_idx = _internal_idx(p.batch, p.m, p.n, p.nnz_total)
@@ -250,9 +311,14 @@ def _build_transpose(p: CsrPattern) -> CsrPattern:
         permT = p.perm.to(odt).index_select(0, permT.long()) if p.perm.dtype != odt else p.perm.index_select(0, permT.long())
     algo = choose_algo(rowptrT, p.batch, p.m, p.nnz_total)
     nnzT = p.nnz_total
-    if algo == nat.ALGO_AUTO and nnzT >= _PAD_MIN_NNZ:
-        rowptrT, colindT, permT, nnzT = _pad_rows(rowptrT, colindT, permT, _ROW_PAD)
-    return _with_split(CsrPattern(rowptrT, colindT, permT, p.batch, p.m, p.n, p.m, 0, nnzT, out_idx, algo=algo, keep=(p,)))
+    patT = CsrPattern(rowptrT, colindT, permT, p.batch, p.m, p.n, p.m, 0, nnzT, out_idx, algo=algo, keep=(p,))
+    if algo == nat.ALGO_AUTO and nnzT >= _PAD_MIN_NNZ and window_plan(patT) is None:
+        # no column-window structure: the row-tile kernels take it, with rows padded to whole gather groups
+        # (skipped if the padding would overflow a 32-bit rowptr)
+        if out_idx == nat.I64 or nnzT + (_ROW_PAD - 1) * p.batch * p.m < _I32_MAX:
+            rowptrT, colindT, permT, nnzT = _pad_rows(rowptrT, colindT, permT, _ROW_PAD)
+            patT = CsrPattern(rowptrT, colindT, permT, p.batch, p.m, p.n, p.m, 0, nnzT, out_idx, algo=algo, keep=(p,))
+    return _with_split(patT)
 
 
 def _split_bound() -> int:
