@@ -63,6 +63,9 @@ CONFIGS = {
                        desc="reference 'large' random case: CSR int64 262144^2, nnz 65536 x dense 262144x512 fp32"),
     "batched128": dict(kind="csr_uniform", n=1024, m=1024, per_row=4, K=64, dtype="f32", batch=128,
                        desc="reference batched random case: batched CSR int32 b=128 1024^2, nnz 4096/item x dense 1024x64 fp32"),
+    # one rank's share of config 2 under 8-way strong scaling (1 of the 8 batch items), for single-GPU tuning runs
+    "2shard8": dict(kind="csr_uniform", n=65536, m=65536, per_row=16, K=128, dtype="f32", batch=1,
+                    desc="one batch item of BASELINE configs[1] (what each of 8 ranks runs under strong scaling)"),
     "5bf16": dict(kind="csr_uniform", n=262144, m=262144, per_row=8, K=512, dtype="bf16", batch=None,
                   desc="CSR 262144^2 8 nnz/row x dense 262144x512 bf16 (BASELINE configs[4])"),
 }
@@ -291,8 +294,8 @@ def describe_config(cfg, args, world):
         sharding = f"nnz-balanced row blocks over {world} ranks, B replicated, grad_B reduce-scatter + all-gather (NCCL)"
     mib = dense_mib_per_rank(cfg, world, scaling, k_sharded)
     flush = mib <= 252
-    l2 = (f"dense operands + outputs of one step = {mib:.0f} MiB per rank fit L2 (126 MB): an L2 flush (256 MiB write) "
-          "runs between timed steps, outside the per-step event pair" if flush else
+    l2 = (f"dense operands + outputs of one step = {mib:.0f} MiB per rank fit L2 (126 MB): an L2 flush "
+          "(a 256 MiB write, then a 256 MiB read that leaves clean lines) runs between timed steps, outside the per-step event pair" if flush else
           f"inputs larger than L2: dense operands + outputs of one step = {mib:.0f} MiB per rank vs 126 MB L2; no explicit flush")
     return ({"workload": cfg["desc"], "config_id": args.config, "K": cfg["K"], "l2": l2, "sharding": sharding},
             scaling, k_sharded, flush)
@@ -412,6 +415,15 @@ def main():
         G = G[bounds[rank]:bounds[rank + 1]].contiguous()
     st = problem_stats(A, cfg["K"])
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush else None
+    flush_src = torch.zeros(64 << 20, dtype=torch.int32, device=dev) if flush else None
+
+    def flush_l2():
+        # evict the step's operands: write a 256 MiB buffer (> 126 MB L2), then stream a second 256 MiB buffer through L2
+        # by reading it, so the cache is left holding clean lines -- after the write alone it holds 126 MB of dirty lines
+        # whose write-back would be charged to the first kernels of the timed step
+        flush_buf.zero_()
+        flush_src.sum()
+
     A.requires_grad_(True)
     B.requires_grad_(True)
     op = D.sparse_mm_row_sharded if row_sharded else D.sparse_mm_k_sharded if k_sharded else sparse_mm
@@ -462,7 +474,7 @@ def main():
             pairs = []
             for _ in range(args.steps):
                 if flush_buf is not None:
-                    flush_buf.zero_()
+                    flush_l2()
                     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     a.record()
                     run_step()

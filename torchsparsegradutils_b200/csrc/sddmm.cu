@@ -333,7 +333,9 @@ static int launch_sddmm_tile(const SddmmParams<V, I>& p, int64_t nnz_total, cuda
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem) != cudaSuccess || occ < 1) occ = 1;
     ctas_per_sm[exact] = occ;
   }
-  const int tile_rows = pick_tile_rows(p.batch * p.n, nnz_total, Cfg::CAP, 256 / LPR, VPL == 1 ? 256 : TSGU_TILE_ROWS_DEFAULT);
+  const int tile_rows = balance_tile_rows(
+      pick_tile_rows(p.batch * p.n, nnz_total, Cfg::CAP, 256 / LPR, VPL == 1 ? 256 : TSGU_TILE_ROWS_DEFAULT), p.n, p.batch,
+      nnz_total, Cfg::CAP, (int64_t)kNumSMs * ctas_per_sm[exact], 256 / LPR);
   const int64_t tiles_per_item = (p.n + tile_rows - 1) / tile_rows;
   const int64_t num_tiles = tiles_per_item * p.batch;
   int64_t grid = (int64_t)kNumSMs * ctas_per_sm[exact];

@@ -328,7 +328,8 @@ static int launch_tile(const SpmmParams<V, I>& p, int64_t nnz_total, cudaStream_
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem) != cudaSuccess || occ < 1) occ = 1;
     ctas_per_sm[exact] = occ;
   }
-  const int tile_rows = pick_tile_rows(p.batch * p.n, nnz_total, Cfg::CAP, 256 / LPR);
+  const int tile_rows = balance_tile_rows(pick_tile_rows(p.batch * p.n, nnz_total, Cfg::CAP, 256 / LPR), p.n, p.batch,
+                                          nnz_total, Cfg::CAP, (int64_t)kNumSMs * ctas_per_sm[exact], 256 / LPR);
   const int64_t tiles_per_item = (p.n + tile_rows - 1) / tile_rows;
   const int64_t num_tiles = tiles_per_item * p.batch;
   int64_t grid = (int64_t)kNumSMs * ctas_per_sm[exact];

@@ -100,6 +100,31 @@ inline int pick_tile_rows(int64_t total_rows, int64_t nnz_total, int cap_entries
   return (int)r;
 }
 
+// Wave quantisation: the persistent kernels hand tiles out round-robin, so every CTA runs floor or ceil(tiles / grid)
+// of them, and inside a tile the lane groups take rows in passes of `groups` rows.  A launch with only a few tiles per
+// CTA (one rank's share of a strongly scaled batch: 65 536 rows = 512 tiles of 128 rows on 296 CTAs -> 2 waves of 4
+// passes where 1.73 waves would do) wastes the difference.  For such launches pick the tile height (a multiple of
+// `groups`, within the staging capacity) that minimises waves x passes; e.g. 224 rows -> 293 tiles -> ONE wave of 7
+// passes.  Launches with >= 4 waves keep the swept default.  (Simply shrinking tiles until there are many waves was
+// measured slower -- 32-row tiles: 0.1455 -> 0.153 ms per step on that shard: the per-tile cost grows.)
+inline int balance_tile_rows(int tile_rows, int64_t rows_per_item, int64_t batch, int64_t nnz_total, int cap_entries,
+                             int64_t grid, int groups) {
+  auto waves = [&](int t) { return (((rows_per_item + t - 1) / t) * batch + grid - 1) / grid; };
+  if (grid <= 0 || rows_per_item <= 0 || waves(tile_rows) >= 4) return tile_rows;
+  const double avg = (double)nnz_total / (double)(rows_per_item * batch);
+  double best_cost = 1e300;
+  int best = tile_rows;
+  for (int t = groups; t <= TSGU_TILE_ROWS; t += groups) {
+    if (t != tile_rows && 1.1 * avg * t > (double)cap_entries) break;  // a tile over the staging capacity falls back to global reads
+    const double cost = (double)waves(t) * ((double)((t + groups - 1) / groups) + 0.5);  // + half a pass of fixed cost per tile
+    if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && abs(t - tile_rows) < abs(best - tile_rows))) {
+      best_cost = cost;
+      best = t;
+    }
+  }
+  return best;
+}
+
 struct TileCoord {
   int64_t item, r0;
   int rows;  // rows in this tile (<= TILE_ROWS)

@@ -19,6 +19,7 @@ grad_B = A^T G          torch.sparse.mm(A.t(), G) (``:229``)             cached 
 """
 from __future__ import annotations
 
+import os
 from typing import cast
 
 import torch
@@ -120,9 +121,41 @@ class SparseMatMul(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad):  # type: ignore[override]
+        if ctx.needs_input_grad[0] and ctx.needs_input_grad[1] and _concurrent_backward_pays(ctx, grad):
+            return _backward_two_streams(ctx, grad)
         gradA = _grad_A(ctx, grad) if ctx.needs_input_grad[0] else None
         gradB = _grad_B(ctx, grad) if ctx.needs_input_grad[1] else None
         return gradA, gradB
+
+
+# grad_A (SDDMM) and grad_B (value gather + transposed SpMM) are independent.  Each is a persistent kernel that owns the
+# whole GPU, so for LARGE problems running them concurrently only makes them share the same L2 bandwidth (measured on
+# BASELINE config 2: 0.930 -> 0.920 ms, config 3: slower).  A SMALL problem -- one rank's share of a strongly scaled
+# batch: 1 M entries, ~45 us per kernel -- spends a third of each kernel ramping up and draining (2 tile waves where
+# 1.73 would do); there the second stream fills those holes.  The threshold is the L2->SM gather volume of one pass.
+_CONCURRENT_BWD_MAX_GATHER_BYTES = int(os.environ.get("TSGU_B200_CONCURRENT_BWD_BYTES", str(3 << 29)))
+_side_streams: dict = {}
+
+
+def _concurrent_backward_pays(ctx, grad) -> bool:
+    pat = ctx.pattern
+    csr = pat if isinstance(pat, CsrPattern) else pat.csr
+    return 0 < csr.nnz_total * grad.shape[-1] * grad.element_size() <= _CONCURRENT_BWD_MAX_GATHER_BYTES
+
+
+def _backward_two_streams(ctx, grad):
+    dev = grad.device
+    main = torch.cuda.current_stream(dev)
+    side = _side_streams.get(dev.index)
+    if side is None:
+        side = _side_streams[dev.index] = torch.cuda.Stream(dev)
+    side.wait_stream(main)  # fork (under graph capture: a parallel branch of the graph)
+    with torch.cuda.stream(side):
+        gradB = _grad_B(ctx, grad)
+    gradA = _grad_A(ctx, grad)
+    main.wait_stream(side)  # join
+    gradB.record_stream(main)
+    return gradA, gradB
 
 
 def _grad_A(ctx, grad):
