@@ -291,7 +291,8 @@ def describe_config(cfg, args, world):
     elif k_sharded:
         sharding = f"dense columns K split over {world} ranks, A replicated, grad_A values all-reduce (NCCL)"
     else:
-        sharding = f"nnz-balanced row blocks over {world} ranks, B replicated, grad_B reduce-scatter + all-gather (NCCL)"
+        sharding = (f"nnz-balanced row blocks over {world} ranks, B replicated, grad_B {args.grad_b} (NCCL"
+                    f"{', not overlapped' if args.no_overlap else ', overlapped with the SDDMM'})")
     mib = dense_mib_per_rank(cfg, world, scaling, k_sharded)
     flush = mib <= 252
     l2 = (f"dense operands + outputs of one step = {mib:.0f} MiB per rank fit L2 (126 MB): an L2 flush "
@@ -341,6 +342,9 @@ def main():
     ap.add_argument("--sharding", default="k", choices=["rows", "k"],
                     help="one large (unbatched) matrix at N > 1: rows = nnz-balanced row blocks, B replicated, grad_B "
                          "reduce-scatter (north_star's scheme); k = dense columns split, A replicated, grad_A all-reduce")
+    ap.add_argument("--grad-b", default="all_reduce", choices=["all_reduce", "reduce_scatter"],
+                    help="row sharding: collective for grad_B (reduce_scatter leaves each rank its block of rows)")
+    ap.add_argument("--no-overlap", action="store_true", help="row sharding: run the SDDMM after the collective finished")
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
                     help="batched configs at N > 1: strong (default) = BASELINE's literal config, its batch items split over "
                          "the ranks; weak = every rank runs a full batch of its own (global batch = batch x N)")
@@ -426,7 +430,11 @@ def main():
 
     A.requires_grad_(True)
     B.requires_grad_(True)
-    op = D.sparse_mm_row_sharded if row_sharded else D.sparse_mm_k_sharded if k_sharded else sparse_mm
+    if row_sharded:
+        def op(a, b):
+            return D.sparse_mm_row_sharded(a, b, grad_b=args.grad_b, overlap=not args.no_overlap)
+    else:
+        op = D.sparse_mm_k_sharded if k_sharded else sparse_mm
 
     def step():
         A.grad = None
@@ -493,7 +501,10 @@ def main():
     timed = {"region": "eager", "ms_total": eager_total}
     # region B: the same step replayed from a CUDA graph (fixed pattern, fixed shapes): no host work between kernels
     graph_note = None
-    if not args.no_graph:
+    if (row_sharded or k_sharded) and not args.no_graph:
+        # a step with a collective inside is not captured: a capture failure on ONE rank would desynchronise the ranks
+        graph_note = {"unavailable": "step contains a NCCL collective: eager region only"}
+    elif not args.no_graph:
         try:
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -529,8 +540,12 @@ def main():
         cnt = torch.tensor([0 if (k_sharded and rank != 0) else st["nnz"], launches], device=dev, dtype=torch.int64)
         dist.all_reduce(cnt)
         nnz_all, launches_all = int(cnt[0]), int(cnt[1])
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, {"kernels_ms": {k: round(v["ms"], 4) for k, v in ksum.items()},
+                                           "nnz": st["nnz"], "rows": st["n"] * st["batch"],
+                                           "host_enqueue_ms": round(host_ms, 4)})
     else:
-        nnz_all, launches_all, host_ms_max = st["nnz"], launches, host_ms
+        nnz_all, launches_all, host_ms_max, per_rank = st["nnz"], launches, host_ms, None
     ms_step = ms_total / args.steps
     value = nnz_all / (ms_step * 1e-3)
 
@@ -594,7 +609,7 @@ def main():
                 "kernels": kernels, "nnz_per_step": nnz_all,
                 "timed_region": timed_region_note, "eager_ms_per_step": eager_total / args.steps, "cuda_graph": graph_note,
                 "host_enqueue_ms_per_step": host_ms_max, "cold_first_step_ms": cold_ms,
-                "cold_pattern_step_ms": cold_pattern_ms, "reference_methodology": ref_meth, "host_affinity": numa}
+                "cold_pattern_step_ms": cold_pattern_ms, "reference_methodology": ref_meth, "host_affinity": numa, "per_rank": per_rank}
         emit_json(line)
     if dist is not None:
         dist.destroy_process_group()

@@ -70,6 +70,11 @@ TSGU_API const char* tsgu_error_string(int code);
 /* Number of kernels this library has launched in the calling process (monotonic;
  * bench.py reports the delta over the timed region as `gpu_launches`). */
 TSGU_API int64_t tsgu_launch_count(void);
+/* SMs the persistent kernels launched from the CALLING THREAD leave free from now on (0 = use all 148); returns the
+ * previous value.  Used while a collective must run concurrently with a kernel of this library (row-sharded
+ * grad_B reduction overlapped with the SDDMM): a persistent grid that owns every SM would otherwise
+ * keep NCCL's kernels waiting until it drains. */
+TSGU_API int tsgu_set_sm_margin(int sms);
 
 /* ------------------------------------------------------------------------------------
  * SpMM:  C[t] = A[t] * B[t]                 replaces torch.sparse.mm(A, B)

@@ -183,3 +183,14 @@ def test_world_size_2_gloo(worker):
         p.join(120)
         assert p.exitcode == 0
     assert out.get() is True
+
+
+def test_row_block_bounds_partition_rows():
+    from torchsparsegradutils_b200.distributed import row_block_bounds
+
+    for m, world in ((10, 4), (4194304, 8), (7, 8), (16, 2)):
+        blocks = [row_block_bounds(m, world, r) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == m
+        assert all(b[0] <= b[1] for b in blocks) and all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+        per = -(-m // world)
+        assert all(b[1] - b[0] <= per for b in blocks)

@@ -42,6 +42,20 @@ def _worker(rank, world, port, out):
         ok = (torch.allclose(C_loc, C[lo:hi], rtol=1e-5, atol=1e-5)
               and torch.allclose(A_loc.grad.values(), A_full.grad.values()[s:e], rtol=1e-5, atol=1e-5)
               and torch.allclose(B_rep.grad, B_full.grad, rtol=1e-5, atol=1e-5))
+        # reduce-scatter mode: this rank's block of rows of grad_B is the full sum, the rest of B.grad is zero
+        A_rs = D.shard_rows_csr(A, lo, hi).requires_grad_(True)
+        B_rs = B.clone().requires_grad_(True)
+        D.sparse_mm_row_sharded(A_rs, B_rs, grad_b="reduce_scatter").backward(G[lo:hi])
+        blo, bhi = D.row_block_bounds(B.shape[0], world, rank)
+        mask = torch.zeros(B.shape[0], dtype=torch.bool, device=dev)
+        mask[blo:bhi] = True
+        ok = (ok and torch.allclose(B_rs.grad[blo:bhi], B_full.grad[blo:bhi], rtol=1e-5, atol=1e-5)
+              and bool((B_rs.grad[~mask] == 0).all()) and torch.allclose(A_rs.grad.values(), A_loc.grad.values()))
+        # not overlapped variant gives the same numbers
+        A_no = D.shard_rows_csr(A, lo, hi).requires_grad_(True)
+        B_no = B.clone().requires_grad_(True)
+        D.sparse_mm_row_sharded(A_no, B_no, overlap=False).backward(G[lo:hi])
+        ok = ok and torch.equal(B_no.grad, B_rep.grad)
         if not ok:
             print("rank", rank, "max diffs", float((C_loc - C[lo:hi]).abs().max()),
                   float((A_loc.grad.values() - A_full.grad.values()[s:e]).abs().max()),

@@ -707,3 +707,29 @@ def test_unsupported_value_dtype_is_a_runtime_error():
     Ah = torch.sparse_csr_tensor(A.crow_indices(), A.col_indices(), A.values().half(), A.shape)
     with pytest.raises(RuntimeError, match="unsupported value dtype"):
         sparse_mm(Ah, torch.rand(8, 4, device=DEV).half())
+
+
+def test_misaligned_csr_views_take_the_fast_kernels_and_match():
+    """CSR arrays that are views at an odd element offset (a row block cut out of a larger matrix): results equal the
+    aligned copy's bit for bit, and the pattern holds aligned copies so that the staged kernels stay eligible."""
+    import torchsparsegradutils_b200 as tsgu
+    from torchsparsegradutils_b200 import sparse_mm
+    from torchsparsegradutils_b200._pattern import csr_pattern
+
+    tsgu.clear_pattern_cache()
+    A = rand_csr(30000, 5000, 9, seed=4)
+    crow, col, val = A.crow_indices(), A.col_indices(), A.values()
+    lo, hi = 7, 30000
+    s, e = int(crow[lo]), int(crow[hi])
+    assert (s * 4) % 16 != 0
+    Av = torch.sparse_csr_tensor((crow[lo:hi + 1] - crow[lo]), col[s:e], val[s:e], (hi - lo, 5000))
+    assert Av.col_indices().data_ptr() % 16 != 0
+    Ac = torch.sparse_csr_tensor((crow[lo:hi + 1] - crow[lo]).clone(), col[s:e].clone(), val[s:e].clone(), (hi - lo, 5000))
+    B = torch.rand(5000, 64, device=DEV)
+    G = torch.rand(hi - lo, 64, device=DEV)
+    C1, gA1, gB1 = _run(Av, B, G)
+    C2, gA2, gB2 = _run(Ac, B, G)
+    assert torch.equal(C1, C2) and torch.equal(gA1.values(), gA2.values()) and torch.equal(gB1, gB2)
+    p = csr_pattern(Av)
+    assert p.colind.data_ptr() % 16 == 0 and p.rowptr.data_ptr() % 16 == 0
+    tsgu.clear_pattern_cache()

@@ -32,6 +32,7 @@ _SIGNATURES = {
     "tsgu_version": (c_int, []),
     "tsgu_error_string": (c_char_p, [_I]),
     "tsgu_launch_count": (_L, []),
+    "tsgu_set_sm_margin": (_I, [_I]),
     "tsgu_spmm_csr": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _I, _I, _P, _Z, _P]),
     "tsgu_spmm_workspace_bytes": (_Z, [_L, _L, _L, _L, _I, _I]),
     "tsgu_sddmm_csr": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _I, _I, _P, _Z, _P]),
@@ -88,6 +89,21 @@ def check(code: int, what: str) -> None:
     if code != 0:
         msg = lib().tsgu_error_string(code)
         raise RuntimeError(f"{what} failed: {msg.decode() if msg else code} (code {code})")
+
+
+class sm_margin:
+    """``with sm_margin(16): ...`` -- persistent kernels launched inside leave that many SMs to concurrent kernels."""
+
+    def __init__(self, sms: int):
+        self.sms = int(sms)
+
+    def __enter__(self):
+        self.prev = lib().tsgu_set_sm_margin(self.sms)
+        return self
+
+    def __exit__(self, *exc):
+        lib().tsgu_set_sm_margin(self.prev)
+        return False
 
 
 def launch_count() -> int:

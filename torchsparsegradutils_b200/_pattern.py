@@ -58,6 +58,13 @@ def set_pattern_cache_capacity(n: int, max_bytes: Optional[int] = None) -> None:
         _evict_locked()
 
 
+def aligned_contiguous(t: torch.Tensor) -> torch.Tensor:
+    """`t` itself if it is contiguous with a 16-byte aligned base, else a fresh (aligned) contiguous copy."""
+    if t.is_contiguous() and t.data_ptr() % 16 == 0:
+        return t
+    return t.clone(memory_format=torch.contiguous_format)
+
+
 def _index_key(t: torch.Tensor) -> tuple:
     """Identity of an index tensor's memory (not of its contents -- see the module docstring)."""
     return (t.data_ptr(), t.numel(), tuple(t.shape), tuple(t.stride()), t.storage_offset(), t.dtype, t._version)
@@ -211,8 +218,11 @@ def choose_algo(rowptr: torch.Tensor, batch: int, n: int, nnz_total: int) -> int
     """Row-split (regular rows) or merge-path (skewed rows) -- decided once per pattern.
 
     Merge-path pays a fix-up pass and per-entry row bookkeeping, so it is only picked when one row
-    is both long in absolute terms and far above the mean (power-law graphs).  One host sync per new
-    pattern.  ``TSGU_B200_ALGO=auto|rowsplit|merge`` overrides the heuristic (benchmarking only).
+    is both long in absolute terms (> 256 entries: it would keep one lane group busy for dozens of gather batches
+    while the rest of its tile idles) and far above the mean (> 16 x).  Power-law graphs qualify, and so does every
+    row block of one: the tail rows of an R-MAT matrix handed to a rank by row sharding still hold rows of several
+    hundred entries among rows of 8 (with the round-1 thresholds, 1024 / 32 x, that shard fell to the row-tile
+    kernels and its rank took 25 ms per step).  One host sync per new pattern.  ``TSGU_B200_ALGO=auto|rowsplit|merge`` overrides the heuristic (benchmarking only).
     """
     forced = _ALGO_ENV.get(os.environ.get("TSGU_B200_ALGO", "auto").lower())
     if forced is not None and forced != nat.ALGO_SPLIT:
@@ -224,7 +234,7 @@ def choose_algo(rowptr: torch.Tensor, batch: int, n: int, nnz_total: int) -> int
     flat = rowptr.reshape(-1)  # batch == 1: torch batched CSR keeps a leading dim of 1
     max_row = int((flat[1:] - flat[:-1]).max())
     mean = nnz_total / n
-    return _SKEWED_ALGO if (max_row > 1024 and max_row > 32 * mean) else nat.ALGO_AUTO
+    return _SKEWED_ALGO if (max_row > 256 and max_row > 16 * mean) else nat.ALGO_AUTO
 
 
 def _internal_idx(batch: int, rows: int, cols: int, nnz: int) -> int:
@@ -398,7 +408,10 @@ def csr_pattern(A: torch.Tensor) -> CsrPattern:
     batched = A.dim() == 3
     batch = A.shape[0] if batched else 1
     n, m = A.shape[-2], A.shape[-1]
-    crow_c, col_c = crow.contiguous(), col.contiguous()
+    # the staged (bulk-copy) kernels need 16-byte aligned array bases; torch allocations are, views into them
+    # (crow[lo:hi], col[s:e] of a row block) need not be: take an aligned copy once per pattern rather than let the
+    # dispatcher fall to the non-staged kernels (measured on a row block of config 4: 15.7 ms instead of 0.93 ms)
+    crow_c, col_c = aligned_contiguous(crow), aligned_contiguous(col)
     nnz_item = col_c.shape[-1]
     pat = _with_split(CsrPattern(crow_c, col_c, None, batch, n, m, n + 1, nnz_item, batch * nnz_item,
                                  nat.idx_enum(crow.dtype), algo=choose_algo(crow_c, batch, n, batch * nnz_item),

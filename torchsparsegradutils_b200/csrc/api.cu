@@ -3,6 +3,13 @@
 
 namespace tsgu {
 unsigned long long g_launches = 0;
+thread_local int g_sm_margin = 0;
+}
+
+extern "C" int tsgu_set_sm_margin(int sms) {
+  const int prev = tsgu::g_sm_margin;
+  tsgu::g_sm_margin = sms < 0 ? 0 : sms;
+  return prev;
 }
 
 extern "C" int tsgu_version(void) { return TSGU_ABI_VERSION; }

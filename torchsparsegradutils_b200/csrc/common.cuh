@@ -20,6 +20,15 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// SMs the persistent kernels leave free (tsgu_set_sm_margin; per calling thread).  A persistent grid of
+// 148 x resident-CTAs owns every SM, so a kernel that should run CONCURRENTLY (NCCL's reduction kernels while the
+// grad_B collective of row sharding overlaps the SDDMM) finds no slot until the grid drains.
+extern thread_local int g_sm_margin;  // defined in api.cu
+inline int64_t persistent_sms() {
+  const int m = g_sm_margin;
+  return m > 0 && m < kNumSMs ? kNumSMs - m : kNumSMs;
+}
+
 // ---------------------------------------------------------------- value-type traits
 template <typename V> struct VT;
 template <> struct VT<float> {

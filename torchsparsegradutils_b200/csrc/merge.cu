@@ -447,7 +447,7 @@ static int launch_spmm_merge(const I* rowptr, const I* colind, const V* vals, co
   if (e != cudaSuccess) return (int)e;
   int occ = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem) != cudaSuccess || occ < 1) occ = 1;
-  int64_t grid = (int64_t)kNumSMs * occ;
+  int64_t grid = persistent_sms() * occ;
   if (grid > num_tiles) grid = num_tiles;
   kern<<<(unsigned)grid, 256, smem, s>>>(p, num_tiles);
   count_launch();
@@ -747,7 +747,7 @@ static int launch_sddmm_merge(const MergeSddmmParams<V, I>& p0, void* ws, size_t
   if (e != cudaSuccess) return (int)e;
   int occ = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem) != cudaSuccess || occ < 1) occ = 1;
-  int64_t grid = (int64_t)kNumSMs * occ;
+  int64_t grid = persistent_sms() * occ;
   if (grid > num_tiles) grid = num_tiles;
   kern<<<(unsigned)grid, 256, smem, s>>>(p, num_tiles);
   count_launch();

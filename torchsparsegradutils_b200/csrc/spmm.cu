@@ -332,7 +332,7 @@ static int launch_tile(const SpmmParams<V, I>& p, int64_t nnz_total, cudaStream_
                                           nnz_total, Cfg::CAP, (int64_t)kNumSMs * ctas_per_sm[exact], 256 / LPR);
   const int64_t tiles_per_item = (p.n + tile_rows - 1) / tile_rows;
   const int64_t num_tiles = tiles_per_item * p.batch;
-  int64_t grid = (int64_t)kNumSMs * ctas_per_sm[exact];
+  int64_t grid = persistent_sms() * ctas_per_sm[exact];
   if (grid > num_tiles) grid = num_tiles;
   const int64_t rowptr_len = p.nnz_bstride > 0 ? p.batch * p.rowptr_bstride : p.batch * p.n + 1;
   kern<<<(unsigned)grid, 256, smem, s>>>(p, tiles_per_item, num_tiles, rowptr_len, nnz_total, tile_rows);

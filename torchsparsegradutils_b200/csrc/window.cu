@@ -670,7 +670,7 @@ static int win_launch(Kern kern, int smem, int64_t num_tiles, cudaStream_t s, in
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TSGU_WIN_CW * 32 + 32, smem) != cudaSuccess || occ < 1) occ = 1;
     *occ_cache = occ;
   }
-  int64_t grid = (int64_t)kNumSMs * *occ_cache;
+  int64_t grid = persistent_sms() * *occ_cache;
   if (grid > num_tiles) grid = num_tiles;
   kern<<<(unsigned)grid, TSGU_WIN_CW * 32 + 32, smem, s>>>(params);
   count_launch();

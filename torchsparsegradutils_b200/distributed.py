@@ -29,7 +29,12 @@ from typing import Callable, List, Optional, Tuple
 import torch
 import torch.distributed as dist
 
+import os
+
+from . import _native
 from .sparse_matmul import SparseMatMul, _grad_A, _grad_B, sparse_mm
+
+_OVERLAP_SM_MARGIN = int(os.environ.get("TSGU_B200_OVERLAP_SM_MARGIN", "20"))
 
 
 # ------------------------------------------------------------------------------ batch sharding
@@ -82,7 +87,9 @@ def shard_rows_csr(A: torch.Tensor, lo: int, hi: int) -> torch.Tensor:
         raise ValueError("shard_rows_csr expects a 2-D CSR tensor")
     crow, col, val = A.crow_indices(), A.col_indices(), A.values()
     s, e = int(crow[lo]), int(crow[hi])
-    return torch.sparse_csr_tensor((crow[lo:hi + 1] - crow[lo]).contiguous(), col[s:e].contiguous(), val[s:e].contiguous(),
+    # clones, not views: a rank keeps only its block alive, and fresh allocations are 16-byte aligned (what the staged
+    # kernels need; a view starting at entry s generally is not)
+    return torch.sparse_csr_tensor((crow[lo:hi + 1] - crow[lo]).contiguous(), col[s:e].clone(), val[s:e].clone(),
                                    (hi - lo, A.shape[1]))
 
 
@@ -101,39 +108,107 @@ class _AllReduceGrad(torch.autograd.Function):
         return grad, None
 
 
+def row_block_bounds(m: int, world: int, rank: int) -> Tuple[int, int]:
+    """Rows [lo, hi) of an (m, K) dense gradient that `rank` owns after a reduce-scatter: equal blocks of
+    ceil(m / world) rows (NCCL's reduce-scatter needs equal counts; the last block may be short)."""
+    per = -(-m // world)
+    lo = min(rank * per, m)
+    return lo, min(lo + per, m)
+
+
+def _reduce_grad_b(gradB: torch.Tensor, group, mode: str, wire_dtype: Optional[torch.dtype]):
+    """Issue the grad_B collective asynchronously.  Returns (work handles, finish) where finish() runs after the
+    handles completed and yields the tensor autograd hands to B.
+
+    mode "all_reduce": every replica of B receives the full sum (NCCL all-reduce; NVLS in-switch reduction where
+        NCCL enables it).
+    mode "reduce_scatter": every rank receives only ITS block of rows of the sum (row_block_bounds) -- half the wire
+        traffic of an all-reduce, for consumers that are themselves sharded (a sharded optimizer).  The returned
+        tensor keeps B's full shape (autograd requires it); rows outside the rank's block are zero.
+    wire_dtype: optionally send a narrower type (torch.bfloat16 for fp32 gradients halves the bytes on the wire;
+        lossy -- opt-in, off by default so that results stay within the fp32 tolerance)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    send = gradB if wire_dtype is None or wire_dtype == gradB.dtype else gradB.to(wire_dtype)
+    if mode == "all_reduce":
+        work = dist.all_reduce(send, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+        def finish():
+            return send if send is gradB else send.to(gradB.dtype)
+
+        return [work], finish
+    if mode != "reduce_scatter":
+        raise ValueError(f"unknown grad_B reduction mode {mode!r}")
+    m = gradB.shape[-2]
+    K = gradB.shape[-1]
+    flat = send.reshape(-1, K)  # (m, K) -- batched operands are not row-sharded
+    per = -(-m // world)
+    if per * world != m:  # pad to equal blocks
+        padded = flat.new_zeros((per * world, K))
+        padded[:m] = flat
+        flat = padded
+    shard = torch.empty((per, K), dtype=flat.dtype, device=flat.device)
+    work = dist.reduce_scatter_tensor(shard, flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+    def finish():
+        lo, hi = row_block_bounds(m, world, rank)
+        out = torch.zeros_like(gradB)
+        out.reshape(-1, K)[lo:hi] = shard[: hi - lo].to(gradB.dtype)
+        return out
+
+    return [work], finish
+
+
 class _RowShardedMatMul(torch.autograd.Function):
-    """sparse_mm on this rank's row block with the grad_B all-reduce issued as soon as the local partial
-    exists, so it travels over NVLink while the SDDMM (grad_A, purely local) is still running."""
+    """sparse_mm on this rank's row block.  Backward: the local grad_B partial is computed first and its collective is
+    issued asynchronously, so it travels over NVLink while the SDDMM (grad_A, purely local) runs (`overlap=False`:
+    the SDDMM runs after the collective has finished -- for A/B measurements of the overlap)."""
 
     @staticmethod
-    def forward(ctx, A_local, B, group):
-        ctx.group = group
+    def forward(ctx, A_local, B, group, mode, wire_dtype, overlap):
+        ctx.group, ctx.mode, ctx.wire_dtype, ctx.overlap = group, mode, wire_dtype, overlap
         return SparseMatMul.forward(ctx, A_local, B)
 
     @staticmethod
     def backward(ctx, grad):  # type: ignore[override]
-        gradB = work = None
+        gradB = None
+        works, finish = [], None
         if ctx.needs_input_grad[1]:
             gradB = _grad_B(ctx, grad).contiguous()
-            work = dist.all_reduce(gradB, op=dist.ReduceOp.SUM, group=ctx.group, async_op=True)
-        gradA = _grad_A(ctx, grad) if ctx.needs_input_grad[0] else None
-        if work is not None:
-            work.wait()
-        return gradA, gradB, None
+            works, finish = _reduce_grad_b(gradB, ctx.group, ctx.mode, ctx.wire_dtype)
+            if not ctx.overlap:
+                for w in works:
+                    w.wait()
+        gradA = None
+        if ctx.needs_input_grad[0]:
+            # leave a few SMs to NCCL's kernels: a persistent SDDMM grid that owns every SM would make the collective
+            # wait until it has drained (measured: no overlap at all, config 5 on 2 GPUs 1.96 ms = kernels + all-reduce)
+            with _native.sm_margin(_OVERLAP_SM_MARGIN if (works and ctx.overlap) else 0):
+                gradA = _grad_A(ctx, grad)
+        if finish is not None:
+            for w in works:
+                w.wait()
+            gradB = finish()
+        return gradA, gradB, None, None, None, None
 
 
 def sparse_mm_row_sharded(A_local: torch.Tensor, B: torch.Tensor, group: Optional[dist.ProcessGroup] = None,
-                          local_mm: Callable[[torch.Tensor, torch.Tensor], torch.Tensor] = sparse_mm) -> torch.Tensor:
+                          local_mm: Callable[[torch.Tensor, torch.Tensor], torch.Tensor] = sparse_mm,
+                          grad_b: str = "all_reduce", wire_dtype: Optional[torch.dtype] = None,
+                          overlap: bool = True) -> torch.Tensor:
     """C_local = A_local @ B for this rank's row block; B is replicated on every rank.
 
-    grad_A_local and C_local stay local; grad_B is all-reduced so every replica of B sees the full
-    A^T G (the only collective on the path).
+    grad_A_local and C_local stay local; grad_B = sum_p A_p^T G_p is the one exchange step of the path:
+    ``grad_b="all_reduce"`` (default) gives every replica of B the full A^T G; ``grad_b="reduce_scatter"`` gives each
+    rank only its block of rows (:func:`row_block_bounds`; the rest of ``B.grad`` is zero) at half the wire traffic.
     """
     distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     if not distributed:
         return local_mm(A_local, B)
     if local_mm is sparse_mm:  # product path: collective overlapped with the SDDMM
-        return _RowShardedMatMul.apply(A_local, B, group)
+        return _RowShardedMatMul.apply(A_local, B, group, grad_b, wire_dtype, overlap)
+    if grad_b != "all_reduce":
+        raise ValueError("an injected local_mm supports grad_b='all_reduce' only")
     return local_mm(A_local, _AllReduceGrad.apply(B, group))
 
 

@@ -25,7 +25,7 @@ from typing import cast
 import torch
 
 from . import _native, _ops
-from ._pattern import CooPattern, CsrPattern, coo_pattern, csr_pattern
+from ._pattern import CooPattern, CsrPattern, aligned_contiguous, coo_pattern, csr_pattern
 
 
 def sparse_mm(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
@@ -101,10 +101,10 @@ class SparseMatMul(torch.autograd.Function):
         coalesced_vals = None
         if A.layout == torch.sparse_csr:
             pat = csr_pattern(A)
-            csr, vals = pat, A.values().contiguous()
+            csr, vals = pat, aligned_contiguous(A.values())
         else:
             pat = coo_pattern(A)
-            csr, vals = pat.csr, A._values().contiguous()
+            csr, vals = pat.csr, aligned_contiguous(A._values())
             if pat.seg is not None:  # batched COO with duplicates: coalesce values onto the unique pattern
                 coalesced_vals = _ops.segment_sum_values(vals, pat.sort_perm, pat.seg, pat.nnz_unique)
                 vals = coalesced_vals
@@ -186,9 +186,9 @@ def _grad_B(ctx, grad):
     if len(saved) > 2:
         vals = saved[2]
     elif is_csr:
-        vals = A.values().contiguous()
+        vals = aligned_contiguous(A.values())
     else:
-        vals = A._values().contiguous()
+        vals = aligned_contiguous(A._values())
     gradB = _ops.spmm(csr.transpose(), vals, grad, tag="spmm_gradB")
     gradB = gradB if ctx.batched else gradB[0]
     if ctx.B_strides is not None:
