@@ -196,6 +196,16 @@ TSGU_API size_t tsgu_csr_transpose_workspace_bytes(int64_t batch, int64_t m, int
 TSGU_API int tsgu_gather_values(const void* in, const void* perm, void* out, int64_t count,
                        int val_dtype, int idx_dtype, void* stream);
 
+/* out[perm[k]] = in[k], every other element of out (out_count elements) zero: the adjoint of tsgu_gather_values for an
+ * injective perm -- the backward of the PairwiseEncoder value assembly (encoders/pairwise_encoder.py:744-749, :837). */
+TSGU_API int tsgu_scatter_values(const void* in, const void* perm, void* out, int64_t count, int64_t out_count,
+                        int val_dtype, int idx_dtype, void* stream);
+
+/* Batched CSR (crow (b, n+1), col (b, nnz)) -> block-diagonal CSR over b*n rows / b*m columns in one pass: the index
+ * arithmetic of sparse_block_diag (utils/utils.py:604-645) as the solves need it (sparse_solve.py:172-174). */
+TSGU_API int tsgu_block_diag_csr(const void* crow, const void* col, int64_t batch, int64_t n, int64_t m, int64_t nnz,
+                        void* crow_out, void* col_out, int idx_dtype, void* stream);
+
 /* Segmented sum of duplicate coordinates: out[u] = sum_{k in [seg[u], seg[u+1])} in[perm[k]]
  * (what coalesce() does to values, utils/utils.py:580). */
 TSGU_API int tsgu_segment_sum_values(const void* in, const void* perm, const void* seg, void* out,

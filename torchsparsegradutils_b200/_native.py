@@ -50,6 +50,8 @@ _SIGNATURES = {
     "tsgu_csr_transpose": (_I, [_P, _P, _L, _L, _L, _L, _L, _L, _I, _P, _P, _P, _I, _P, _Z, _P]),
     "tsgu_csr_transpose_workspace_bytes": (_Z, [_L, _L, _L, _I]),
     "tsgu_gather_values": (_I, [_P, _P, _P, _L, _I, _I, _P]),
+    "tsgu_scatter_values": (_I, [_P, _P, _P, _L, _L, _I, _I, _P]),
+    "tsgu_block_diag_csr": (_I, [_P, _P, _L, _L, _L, _L, _P, _P, _I, _P]),
     "tsgu_segment_sum_values": (_I, [_P, _P, _P, _P, _L, _I, _I, _P]),
     "tsgu_pack_dense": (_I, [_P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _P]),
     "tsgu_window_limits": (_I, [_P, _P, _P, _P]),

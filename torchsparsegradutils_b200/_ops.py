@@ -369,3 +369,27 @@ def gather_values(vals: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
                                                    nat.val_enum(vals.dtype), nat.idx_enum(perm.dtype),
                                                    nat.stream_ptr(vals.device)), "tsgu_gather_values")
     return out
+
+
+def scatter_values(vals: torch.Tensor, perm: torch.Tensor, out_count: int) -> torch.Tensor:
+    """out[perm[k]] = vals[k], zeros elsewhere (adjoint of gather_values for an injective perm)."""
+    out = torch.empty(out_count, dtype=vals.dtype, device=vals.device)
+    with _on(vals.device):
+        nat.check(nat.lib().tsgu_scatter_values(vals.data_ptr(), perm.data_ptr(), out.data_ptr(), perm.numel(), out_count,
+                                                nat.val_enum(vals.dtype), nat.idx_enum(perm.dtype),
+                                                nat.stream_ptr(vals.device)), "tsgu_scatter_values")
+    return out
+
+
+def block_diag_csr(crow: torch.Tensor, col: torch.Tensor, m: int):
+    """Batched CSR index tensors (b, n+1) / (b, nnz) -> block-diagonal (b*n+1,), (b*nnz,) in one kernel."""
+    b, n1 = crow.shape
+    nnz = col.shape[1]
+    crow, col = crow.contiguous(), col.contiguous()
+    crow_out = torch.empty(b * (n1 - 1) + 1, dtype=crow.dtype, device=crow.device)
+    col_out = torch.empty(b * nnz, dtype=col.dtype, device=col.device)
+    with _on(crow.device):
+        nat.check(nat.lib().tsgu_block_diag_csr(crow.data_ptr(), col.data_ptr(), b, n1 - 1, m, nnz, crow_out.data_ptr(),
+                                                col_out.data_ptr(), nat.idx_enum(crow.dtype), nat.stream_ptr(crow.device)),
+                  "tsgu_block_diag_csr")
+    return crow_out, col_out

@@ -254,6 +254,39 @@ __global__ void __launch_bounds__(256) gather_values_kernel(const V* __restrict_
   }
 }
 
+// out[perm[k]] = in[k]: the adjoint of gather_values for an injective `perm` (out is zero-filled by the launcher).
+template <typename V, typename I>
+__global__ void __launch_bounds__(256) scatter_values_kernel(const V* __restrict__ in, const I* __restrict__ perm,
+                                                             V* __restrict__ out, int64_t count) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t dst = (int64_t)__ldg(perm + k);
+    if (dst >= 0) out[dst] = in[k];
+  }
+}
+
+// Batched CSR (b, n+1) / (b, nnz) -> the block-diagonal CSR over b*n rows and b*m columns that the reference assembles
+// item by item (utils/utils.py:604-645): crow_out[t*n + r] = crow[t, r] + t*nnz, col_out[t*nnz + e] = col[t, e] + t*m.
+template <typename I>
+__global__ void __launch_bounds__(256) block_diag_csr_kernel(const I* __restrict__ crow, const I* __restrict__ col,
+                                                             int64_t batch, int64_t n, int64_t m, int64_t nnz,
+                                                             I* __restrict__ crow_out, I* __restrict__ col_out) {
+  const int64_t total = batch * n + 1 + batch * nnz;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i <= batch * n) {
+      if (i == batch * n) {
+        crow_out[i] = (I)(batch * nnz);
+      } else {
+        const int64_t t = i / n, r = i - t * n;
+        crow_out[i] = (I)((int64_t)crow[t * (n + 1) + r] + t * nnz);
+      }
+    } else {
+      const int64_t e = i - (batch * n + 1);
+      const int64_t t = e / nnz;
+      col_out[e] = (I)((int64_t)col[e] + t * m);
+    }
+  }
+}
+
 template <typename V, typename I>
 __global__ void segment_sum_kernel(const V* __restrict__ in, const I* __restrict__ perm, const I* __restrict__ seg,
                                    V* __restrict__ out, int64_t nseg) {
@@ -486,6 +519,36 @@ extern "C" int tsgu_gather_values(const void* in, const void* perm, void* out, i
     gather_values_kernel<V, I><<<blocks_for((count + 3) / 4, 256), 256, 0, s>>>((const V*)in, (const I*)perm, (V*)out, count);
     count_launch();
   }));
+  return launch_status();
+}
+
+extern "C" int tsgu_scatter_values(const void* in, const void* perm, void* out, int64_t count, int64_t out_count,
+                                   int val_dtype, int idx_dtype, void* stream) {
+  if (count < 0 || out_count < 0) return TSGU_ERR_SHAPE;
+  cudaStream_t s = as_stream(stream);
+  TSGU_DISPATCH_VAL(val_dtype, TSGU_DISPATCH_IDX(idx_dtype, {
+    if (out_count > 0) {
+      cudaError_t e = cudaMemsetAsync(out, 0, (size_t)out_count * sizeof(V), s);
+      if (e != cudaSuccess) return (int)e;
+    }
+    if (count > 0) {
+      scatter_values_kernel<V, I><<<blocks_for(count, 256), 256, 0, s>>>((const V*)in, (const I*)perm, (V*)out, count);
+      count_launch();
+    }
+  }));
+  return launch_status();
+}
+
+extern "C" int tsgu_block_diag_csr(const void* crow, const void* col, int64_t batch, int64_t n, int64_t m, int64_t nnz,
+                                   void* crow_out, void* col_out, int idx_dtype, void* stream) {
+  if (batch < 1 || n < 0 || m < 0 || nnz < 0) return TSGU_ERR_SHAPE;
+  if (idx_dtype == TSGU_I32 && (batch * nnz > 0x7fffffffLL || batch * m > 0x7fffffffLL)) return TSGU_ERR_RANGE;
+  cudaStream_t s = as_stream(stream);
+  TSGU_DISPATCH_IDX(idx_dtype, {
+    block_diag_csr_kernel<I><<<blocks_for(batch * n + 1 + batch * nnz, 256), 256, 0, s>>>(
+        (const I*)crow, (const I*)col, batch, n, m, nnz, (I*)crow_out, (I*)col_out);
+    count_launch();
+  });
   return launch_status();
 }
 
