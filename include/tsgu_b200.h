@@ -95,6 +95,14 @@ TSGU_API int tsgu_spmm_csr(const void* rowptr, const void* colind, const void* v
                   int64_t c_bs, int64_t ldc,
                   int val_dtype, int idx_dtype, int algo,
                   void* workspace, size_t workspace_bytes, void* stream);
+/* Same product over a structure whose rows were PERMUTED (the cached transpose keeps its rows sorted by length so that
+ * the rows a warp works on together are equally long): CSR row s of item t is row row_map[t*n + s] of C[t]
+ * (idx_dtype, a permutation of 0..n-1 per item).  Row-tile and row-split kernels only (algo AUTO / ROWSPLIT). */
+TSGU_API int tsgu_spmm_csr_rowmap(const void* rowptr, const void* colind, const void* vals, const void* perm,
+                         const void* row_map, const void* B, void* C, int64_t batch, int64_t n, int64_t m, int64_t K,
+                         int64_t rowptr_bstride, int64_t nnz_bstride, int64_t nnz_total, int64_t b_bs, int64_t b_rs,
+                         int64_t b_cs, int64_t c_bs, int64_t ldc, int val_dtype, int idx_dtype, int algo, void* stream);
+
 TSGU_API size_t tsgu_spmm_workspace_bytes(int64_t batch, int64_t n, int64_t K, int64_t nnz_total,
                                  int val_dtype, int algo);
 

@@ -34,6 +34,7 @@ _SIGNATURES = {
     "tsgu_launch_count": (_L, []),
     "tsgu_set_sm_margin": (_I, [_I]),
     "tsgu_spmm_csr": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _I, _I, _P, _Z, _P]),
+    "tsgu_spmm_csr_rowmap": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _I, _I, _P]),
     "tsgu_spmm_workspace_bytes": (_Z, [_L, _L, _L, _L, _I, _I]),
     "tsgu_sddmm_csr": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _I, _I, _P, _Z, _P]),
     "tsgu_sddmm_workspace_bytes": (_Z, [_L, _L, _L, _I]),

@@ -57,8 +57,28 @@ def _on(dev: torch.device):
     return _NULL if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
 
 
+_NVTX = os.environ.get("TSGU_B200_NVTX", "0") == "1"
+
+
+class _nvtx_range:
+    """NVTX range around one entry point (profiler hooks); TSGU_B200_NVTX=1 turns them on."""
+
+    def __init__(self, tag, inner):
+        self.tag, self.inner = tag, inner
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push("tsgu_b200::" + self.tag)
+        return self.inner.__enter__()
+
+    def __exit__(self, *exc):
+        r = self.inner.__exit__(*exc)
+        torch.cuda.nvtx.range_pop()
+        return r
+
+
 def _timer(tag: str, dev: torch.device):
-    return _timed(tag, dev) if KernelTimer.active is not None else _NULL
+    t = _timed(tag, dev) if KernelTimer.active is not None else _NULL
+    return _nvtx_range(tag, t) if _NVTX else t
 
 
 class _timed:
@@ -179,6 +199,7 @@ def wants_pregather(pat: CsrPattern) -> bool:
     return pat.perm is not None and pat.nnz_total >= _PREGATHER_MIN_NNZ and pat.algo != nat.ALGO_SPLIT
 
 
+_KSLICE_SORTED = os.environ.get("TSGU_B200_KSLICE_SORTED", "0") == "1"
 _WINDOW_ROW_BYTES = (64, 128, 256)  # dense row widths the column-window kernels are built for (csrc/window.cu)
 _WINDOW_PERM_IN_KERNEL = os.environ.get("TSGU_B200_WINDOW_PERM", "0") == "1"
 
@@ -244,8 +265,16 @@ def spmm(pat: CsrPattern, vals: torch.Tensor, dense: torch.Tensor, algo: Optiona
         with _timer(tag + "_gather", dev):
             vals = gather_values(vals.reshape(-1), perm)
         perm = None
-    if (algo == nat.ALGO_AUTO and pat.m * K * dense.element_size() > (_l2_bytes(dev) * 3) // 5 and pat.uniform_rows):
+    if (algo == nat.ALGO_AUTO and pat.m * K * dense.element_size() > (_l2_bytes(dev) * 3) // 5
+            and (pat.uniform_rows or (_KSLICE_SORTED and pat.row_map is not None))):
         algo |= nat.ALGO_FLAG_KSLICE  # dense operand exceeds L2 and the rows are uniform: L2-resident K slices
+    if pat.row_map is not None:  # a transpose with length-sorted rows
+        with _on(dev), _timer(tag, dev):
+            nat.check(L.tsgu_spmm_csr_rowmap(nat.ptr(pat.rowptr), nat.ptr(pat.colind), nat.ptr(vals), nat.ptr(perm),
+                                             nat.ptr(pat.row_map), dense.data_ptr(), out.data_ptr(), pat.batch, pat.n, pat.m,
+                                             K, pat.rowptr_bstride, pat.nnz_bstride, pat.nnz_total, *_strides(dense),
+                                             pat.n * K, K, vdt, pat.idx, algo, nat.stream_ptr(dev)), "tsgu_spmm_csr_rowmap")
+        return out
     with _on(dev), _timer(tag, dev):
         ws_bytes = L.tsgu_spmm_workspace_bytes(pat.batch, pat.n, K, pat.nnz_total, vdt, algo) if algo == nat.ALGO_MERGE else 0
         ws = nat.workspace(ws_bytes, dev) if ws_bytes else None

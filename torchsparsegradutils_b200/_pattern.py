@@ -138,6 +138,7 @@ class CsrPattern:
     algo: int = nat.ALGO_AUTO  # kernel family chosen once per pattern from its row-length skew
     split: Optional["SplitRows"] = None  # virtual-row view of a skewed pattern (algo == ALGO_SPLIT)
     keep: tuple = ()  # tensors whose storage must outlive this pattern (cache-key owners)
+    row_map: Optional[torch.Tensor] = None  # rows were permuted: CSR row s of item t is output row row_map[t*n + s]
     extras: dict = field(default_factory=dict, repr=False)  # per-pattern plans built lazily by _ops (window plans, ...)
     fingerprint: Optional[torch.Tensor] = field(default=None, repr=False)
     cache_key: Optional[tuple] = field(default=None, repr=False)
@@ -323,11 +324,17 @@ def _build_transpose(p: CsrPattern) -> CsrPattern:
     nnzT = p.nnz_total
     patT = CsrPattern(rowptrT, colindT, permT, p.batch, p.m, p.n, p.m, 0, nnzT, out_idx, algo=algo, keep=(p,))
     if algo == nat.ALGO_AUTO and nnzT >= _PAD_MIN_NNZ and window_plan(patT) is None:
-        # no column-window structure: the row-tile kernels take it, with rows padded to whole gather groups
-        # (skipped if the padding would overflow a 32-bit rowptr)
+        # no column-window structure: the row-tile kernels take it.  Two layout optimisations of a structure WE own:
+        # rows sorted by length inside every item (the 4 rows a warp works on together then hold the same number of
+        # entries: Poisson-distributed lengths otherwise cost max-of-4 instead of the mean), and rows padded to whole
+        # gather groups (skipped if the padding would overflow a 32-bit rowptr)
+        row_map = None
+        if _SORT_ROWS:
+            rowptrT, colindT, permT, row_map = _sort_rows_by_length(rowptrT, colindT, permT, p.batch, p.m)
         if out_idx == nat.I64 or nnzT + (_ROW_PAD - 1) * p.batch * p.m < _I32_MAX:
             rowptrT, colindT, permT, nnzT = _pad_rows(rowptrT, colindT, permT, _ROW_PAD)
-            patT = CsrPattern(rowptrT, colindT, permT, p.batch, p.m, p.n, p.m, 0, nnzT, out_idx, algo=algo, keep=(p,))
+        patT = CsrPattern(rowptrT, colindT, permT, p.batch, p.m, p.n, p.m, 0, nnzT, out_idx, algo=algo, keep=(p,),
+                          row_map=row_map)
     return _with_split(patT)
 
 
@@ -339,6 +346,41 @@ def _with_split(pat: CsrPattern) -> CsrPattern:
     if pat.algo == nat.ALGO_SPLIT and pat.batch == 1:
         pat.split = build_split_rows(pat.rowptr, pat.n, pat.nnz_total, _split_bound())
     return pat
+
+
+_SORT_ROWS = os.environ.get("TSGU_B200_SORT_ROWS", "1") != "0"
+
+
+_SORT_BLOCK = 64  # rows per sorting block: a multiple of the rows one pass of a CTA's lane groups covers (32 or 64)
+
+
+def _sort_rows_by_length(rowptr: torch.Tensor, colind: torch.Tensor, perm: torch.Tensor, batch: int, rows_per_item: int):
+    """Reorder the rows of a flat CSR (batch * rows_per_item rows) by length inside blocks of _SORT_BLOCK consecutive rows,
+    alternately descending and ascending ("snake"); returns the reordered (rowptr, colind, perm) and
+    row_map[t * rows + s] = original row (local to the item) at slot s.
+
+    The kernels give a warp 4 (or 8) CONSECUTIVE rows per pass and the warp advances in lock step, so a warp costs
+    the longest of its rows: with Poisson-distributed lengths (a transposed uniform pattern) max-of-4 is ~30 % above
+    the mean.  After the block sort a warp's rows are neighbours in length.  Sorting inside small blocks -- instead of
+    globally -- keeps every tile's entry count at the average (a globally sorted structure puts all long rows into the
+    first tiles, which then overflow the staging buffers), and the alternating direction gives every warp long rows in
+    one pass and short ones in the next.  One-off per pattern, no host sync (the entry count does not change)."""
+    dev, idt = rowptr.device, rowptr.dtype
+    rows = batch * rows_per_item
+    lens = (rowptr[1:] - rowptr[:-1]).long()
+    r = torch.arange(rows, device=dev)
+    local = r % rows_per_item
+    block = (r // rows_per_item) * (-(-rows_per_item // _SORT_BLOCK)) + local // _SORT_BLOCK
+    longest = lens.max()  # stays on the device
+    sub = torch.where(block % 2 == 0, longest - lens, lens)
+    order = torch.argsort(block * (longest + 1) + sub, stable=True)
+    new_lens = lens[order]
+    new_rowptr = torch.zeros(rows + 1, dtype=torch.int64, device=dev)
+    new_rowptr[1:] = new_lens.cumsum(0)
+    nnz = colind.numel()
+    slot = torch.repeat_interleave(r, new_lens, output_size=nnz)
+    pos = torch.arange(nnz, device=dev) - new_rowptr[slot] + rowptr.long()[order][slot]
+    return new_rowptr.to(idt), colind[pos], perm[pos], (order % rows_per_item).to(idt)
 
 
 _ROW_PAD = 4          # the row-split kernels consume a row in groups of >= 4 entries

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) spmm_rowsplit_kernel(const SpmmParams<V, 
     const int64_t e0 = (int64_t)__ldg(rp) + item * p.nnz_bstride;
     const int64_t e1 = (int64_t)__ldg(rp + 1) + item * p.nnz_bstride;
     const V* Bi = p.B + item * p.b_bs;
-    V* Crow = p.C + item * p.c_bs + lr * p.ldc;
+    V* Crow = p.C + item * p.c_bs + (p.row_map ? (int64_t)p.row_map[r] : lr) * p.ldc;
 
     for (int64_t k0 = 0; k0 < p.K; k0 += CHUNK) {
       Acc acc[VPL][EPV];
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(256, TSGU_TILE_MINB(VPL)) spmm_tile_kernel(con
         }
       }
       int64_t dest = c.r0 + lr;
-      if (p.row_map) dest = (int64_t)p.row_map[dest];
+      if (p.row_map) dest = (int64_t)p.row_map[c.item * p.n + dest];
       if (dest >= 0) {
         V* Crow = p.C + c.item * p.c_bs + dest * p.ldc;
 #pragma unroll
@@ -435,6 +435,28 @@ extern "C" int tsgu_spmm_csr(const void* rowptr, const void* colind, const void*
     p.b_bs = b_bs; p.b_rs = b_rs; p.b_cs = b_cs; p.c_bs = c_bs; p.ldc = ldc;
     p.row_map = nullptr; p.partials = nullptr;
     return tsgu::spmm_dispatch<V, I>(p, m, nnz_total, algo, workspace, workspace_bytes, tsgu::as_stream(stream));
+  }));
+  return 0;
+}
+
+extern "C" int tsgu_spmm_csr_rowmap(const void* rowptr, const void* colind, const void* vals, const void* perm,
+                                    const void* row_map, const void* B, void* C, int64_t batch, int64_t n, int64_t m,
+                                    int64_t K, int64_t rowptr_bstride, int64_t nnz_bstride, int64_t nnz_total, int64_t b_bs,
+                                    int64_t b_rs, int64_t b_cs, int64_t c_bs, int64_t ldc, int val_dtype, int idx_dtype,
+                                    int algo, void* stream) {
+  if (batch < 0 || n < 0 || K < 0) return TSGU_ERR_SHAPE;
+  const int family = algo & ~TSGU_ALGO_FLAG_KSLICE;
+  if (family != TSGU_ALGO_AUTO && family != TSGU_ALGO_ROWSPLIT) return TSGU_ERR_ALGO;  // merge-path has no row map
+  if (batch == 0 || n == 0 || K == 0) return 0;
+  TSGU_DISPATCH_VAL(val_dtype, TSGU_DISPATCH_IDX(idx_dtype, {
+    tsgu::SpmmParams<V, I> p;
+    p.rowptr = (const I*)rowptr; p.colind = (const I*)colind; p.vals = (const V*)vals;
+    p.perm = (const I*)perm; p.B = (const V*)B; p.C = (V*)C;
+    p.batch = batch; p.n = n; p.K = K;
+    p.rowptr_bstride = rowptr_bstride; p.nnz_bstride = nnz_bstride;
+    p.b_bs = b_bs; p.b_rs = b_rs; p.b_cs = b_cs; p.c_bs = c_bs; p.ldc = ldc;
+    p.row_map = (const I*)row_map; p.partials = nullptr;
+    return tsgu::spmm_dispatch<V, I>(p, m, nnz_total, algo, nullptr, 0, tsgu::as_stream(stream));
   }));
   return 0;
 }
