@@ -237,15 +237,39 @@ template <typename V, typename I>
 __global__ void __launch_bounds__(256) gather_values_kernel(const V* __restrict__ in, const I* __restrict__ perm,
                                                             V* __restrict__ out, int64_t count) {
   const int64_t quads = count / 4;
+  // the four permutation entries of a quad are one vector load and the four results one vector store when the arrays
+  // are suitably aligned (they are: torch allocations): half the LSU instructions of the scalar version, which was
+  // throttled by the LSU queues (ncu: mio_throttle 17.8, lg_throttle 6.6 stall cycles per issue)
+  const bool vec_p = (reinterpret_cast<uintptr_t>(perm) % (4 * sizeof(I))) == 0;
+  const bool vec_o = (reinterpret_cast<uintptr_t>(out) % (4 * sizeof(V))) == 0;
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (int64_t)gridDim.x * blockDim.x) {
     int64_t src[4];
+    if (vec_p) {
+      if constexpr (sizeof(I) == 4) {
+        const int4 p4 = __ldg(reinterpret_cast<const int4*>(perm) + q);
+        src[0] = p4.x; src[1] = p4.y; src[2] = p4.z; src[3] = p4.w;
+      } else {
+        const longlong2 a = __ldg(reinterpret_cast<const longlong2*>(perm) + 2 * q);
+        const longlong2 b = __ldg(reinterpret_cast<const longlong2*>(perm) + 2 * q + 1);
+        src[0] = a.x; src[1] = a.y; src[2] = b.x; src[3] = b.y;
+      }
+    } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) src[i] = (int64_t)__ldg(perm + 4 * q + i);
+      for (int i = 0; i < 4; ++i) src[i] = (int64_t)__ldg(perm + 4 * q + i);
+    }
     V v[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = src[i] >= 0 ? __ldg(in + src[i]) : VT<V>::from_acc(0);
+    if (vec_o) {
+      struct alignas(4 * sizeof(V)) Quad { V x[4]; };
+      Quad o;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) out[4 * q + i] = v[i];
+      for (int i = 0; i < 4; ++i) o.x[i] = v[i];
+      reinterpret_cast<Quad*>(out)[q] = o;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) out[4 * q + i] = v[i];
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x < (count & 3)) {  // tail
     const int64_t k = quads * 4 + threadIdx.x;
