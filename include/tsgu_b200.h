@@ -227,6 +227,14 @@ TSGU_API int tsgu_pack_dense(const void* src, void* dst, int64_t batch, int64_t 
                     int64_t s_bs, int64_t s_rs, int64_t s_cs, int64_t d_bs, int64_t d_rs, int64_t d_cs,
                     int val_dtype, void* stream);
 
+/* tsgu_pack_dense with an additive epilogue: dst[t, r, c] = src[t, r, c] + add[t, r, c] + rowvec[t, r], `add` (nullable)
+ * addressed with the destination's strides, `rowvec` (nullable) with (v_bs, v_rs).  One pass for the layout change
+ * and the two elementwise adds that follow sparse_mm in SparseMultivariateNormal.rsample
+ * (distributions/sparse_multivariate_normal.py:362 "+ eta", :389 "loc +", after the .t() / permute of :96-100). */
+TSGU_API int tsgu_pack_dense_add(const void* src, const void* add, const void* rowvec, void* dst, int64_t batch,
+                        int64_t rows, int64_t cols, int64_t s_bs, int64_t s_rs, int64_t s_cs, int64_t d_bs,
+                        int64_t d_rs, int64_t d_cs, int64_t v_bs, int64_t v_rs, int val_dtype, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Column-window kernels for structured (banded / stencil) patterns -- same products as
  * tsgu_spmm_csr / tsgu_sddmm_csr (sparse_matmul.py:155, :229, :190-205), for patterns

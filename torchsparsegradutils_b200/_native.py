@@ -55,6 +55,7 @@ _SIGNATURES = {
     "tsgu_block_diag_csr": (_I, [_P, _P, _L, _L, _L, _L, _P, _P, _I, _P]),
     "tsgu_segment_sum_values": (_I, [_P, _P, _P, _P, _L, _I, _I, _P]),
     "tsgu_pack_dense": (_I, [_P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _P]),
+    "tsgu_pack_dense_add": (_I, [_P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _P]),
     "tsgu_window_limits": (_I, [_P, _P, _P, _P]),
     "tsgu_window_plan": (_I, [_P, _P, _L, _L, _L, _L, _I, _I, _P, _P, _P, _P]),
     "tsgu_spmm_window": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _I, _L, _L, _L, _L, _I, _I, _P]),

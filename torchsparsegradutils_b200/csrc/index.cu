@@ -329,16 +329,37 @@ __global__ void segment_sum_kernel(const V* __restrict__ in, const I* __restrict
 // row-major <-> column-major (transposed-view) conversions are coalesced on both sides with
 // PACK_R/8 independent loads per thread in flight.
 constexpr int PACK_R = 128;
+// Optional epilogue operands (tsgu_pack_dense_add): dst = src + add + rowvec[row], where `add` has the destination's
+// element strides and `rowvec` is one value per (item, row).
 template <typename V>
+struct PackAdd {
+  const V* add;     // nullable, addressed with the destination strides
+  const V* rowvec;  // nullable
+  int64_t v_bs, v_rs;
+};
+
+template <typename V, bool ADD = false>
 __global__ void __launch_bounds__(256) pack_dense_kernel(const V* __restrict__ src, V* __restrict__ dst, int64_t rows,
                                                          int64_t cols, int64_t s_bs, int64_t s_rs, int64_t s_cs,
                                                          int64_t d_bs, int64_t d_rs, int64_t d_cs,
-                                                         int64_t blocks_per_item) {
+                                                         int64_t blocks_per_item, PackAdd<V> ep = PackAdd<V>{}) {
+  using Acc = typename VT<V>::Acc;
   __shared__ V tile[PACK_R][33];
   const int64_t item = blockIdx.x / blocks_per_item;
   const int64_t r0 = (blockIdx.x - item * blocks_per_item) * PACK_R;
   const V* sp = src + item * s_bs;
   V* dp = dst + item * d_bs;
+  auto put = [&](int r, int c, int64_t c0) {
+    const int64_t off = (r0 + r) * d_rs + (c0 + c) * d_cs;
+    if constexpr (ADD) {
+      Acc x = VT<V>::to_acc(tile[r][c]);
+      if (ep.add) x += VT<V>::to_acc(ep.add[item * d_bs + off]);
+      if (ep.rowvec) x += VT<V>::to_acc(ep.rowvec[item * ep.v_bs + (r0 + r) * ep.v_rs]);
+      dp[off] = VT<V>::from_acc(x);
+    } else {
+      dp[off] = tile[r][c];
+    }
+  };
   const bool src_row_fast = s_rs < s_cs;  // contiguous along rows (column-major view)
   const bool dst_row_fast = d_rs < d_cs;
   for (int64_t c0 = 0; c0 < cols; c0 += 32) {
@@ -355,11 +376,11 @@ __global__ void __launch_bounds__(256) pack_dense_kernel(const V* __restrict__ s
     if (dst_row_fast) {
       const int r = threadIdx.x % PACK_R;
       for (int c = threadIdx.x / PACK_R; c < 32; c += 256 / PACK_R)
-        if (r0 + r < rows && c0 + c < cols) dp[(r0 + r) * d_rs + (c0 + c) * d_cs] = tile[r][c];
+        if (r0 + r < rows && c0 + c < cols) put(r, c, c0);
     } else {
       const int c = threadIdx.x % 32;
       for (int r = threadIdx.x / 32; r < PACK_R; r += 8)
-        if (r0 + r < rows && c0 + c < cols) dp[(r0 + r) * d_rs + (c0 + c) * d_cs] = tile[r][c];
+        if (r0 + r < rows && c0 + c < cols) put(r, c, c0);
     }
     __syncthreads();
   }
@@ -599,6 +620,24 @@ extern "C" int tsgu_pack_dense(const void* src, void* dst, int64_t batch, int64_
   if (blocks > 0x7fffffffLL) return TSGU_ERR_RANGE;
   TSGU_DISPATCH_VAL(val_dtype, {
     pack_dense_kernel<V><<<(unsigned)blocks, 256, 0, s>>>((const V*)src, (V*)dst, rows, cols, s_bs, s_rs, s_cs, d_bs, d_rs, d_cs, bpi);
+    count_launch();
+  });
+  return launch_status();
+}
+
+extern "C" int tsgu_pack_dense_add(const void* src, const void* add, const void* rowvec, void* dst, int64_t batch,
+                                   int64_t rows, int64_t cols, int64_t s_bs, int64_t s_rs, int64_t s_cs, int64_t d_bs,
+                                   int64_t d_rs, int64_t d_cs, int64_t v_bs, int64_t v_rs, int val_dtype, void* stream) {
+  if (batch < 0 || rows < 0 || cols < 0) return TSGU_ERR_SHAPE;
+  if (batch == 0 || rows == 0 || cols == 0) return 0;
+  cudaStream_t s = as_stream(stream);
+  const int64_t bpi = (rows + PACK_R - 1) / PACK_R;
+  const int64_t blocks = batch * bpi;
+  if (blocks > 0x7fffffffLL) return TSGU_ERR_RANGE;
+  TSGU_DISPATCH_VAL(val_dtype, {
+    PackAdd<V> ep{(const V*)add, (const V*)rowvec, v_bs, v_rs};
+    pack_dense_kernel<V, true><<<(unsigned)blocks, 256, 0, s>>>((const V*)src, (V*)dst, rows, cols, s_bs, s_rs, s_cs, d_bs,
+                                                                 d_rs, d_cs, bpi, ep);
     count_launch();
   });
   return launch_status();
