@@ -362,15 +362,28 @@ __global__ void __launch_bounds__(256) pack_dense_kernel(const V* __restrict__ s
   };
   const bool src_row_fast = s_rs < s_cs;  // contiguous along rows (column-major view)
   const bool dst_row_fast = d_rs < d_cs;
+  constexpr int NIT = PACK_R * 32 / 256;  // elements per thread and chunk (16)
   for (int64_t c0 = 0; c0 < cols; c0 += 32) {
+    // all of a thread's loads are issued before the first shared-memory store (16 independent loads in flight)
+    V tmp[NIT];
     if (src_row_fast) {
-      const int r = threadIdx.x % PACK_R;
-      for (int c = threadIdx.x / PACK_R; c < 32; c += 256 / PACK_R)
-        if (r0 + r < rows && c0 + c < cols) tile[r][c] = sp[(r0 + r) * s_rs + (c0 + c) * s_cs];
+      const int r = threadIdx.x % PACK_R, cb = threadIdx.x / PACK_R;
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        const int c = cb + i * (256 / PACK_R);
+        tmp[i] = (r0 + r < rows && c0 + c < cols) ? __ldg(sp + (r0 + r) * s_rs + (c0 + c) * s_cs) : VT<V>::from_acc(0);
+      }
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) tile[r][cb + i * (256 / PACK_R)] = tmp[i];
     } else {
-      const int c = threadIdx.x % 32;
-      for (int r = threadIdx.x / 32; r < PACK_R; r += 8)
-        if (r0 + r < rows && c0 + c < cols) tile[r][c] = sp[(r0 + r) * s_rs + (c0 + c) * s_cs];
+      const int c = threadIdx.x % 32, rb = threadIdx.x / 32;
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        const int r = rb + i * 8;
+        tmp[i] = (r0 + r < rows && c0 + c < cols) ? __ldg(sp + (r0 + r) * s_rs + (c0 + c) * s_cs) : VT<V>::from_acc(0);
+      }
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) tile[rb + i * 8][c] = tmp[i];
     }
     __syncthreads();
     if (dst_row_fast) {
