@@ -249,7 +249,9 @@ TSGU_API int tsgu_pack_dense_add(const void* src, const void* add, const void* r
  *   stats int32[4]: tiles that do not fit, max distinct columns, max runs, max entries per tile
  * The plan is usable iff stats[0] == 0.  32-bit index structures only (idx_dtype == TSGU_I32
  * for the compute entry points).  The compute kernels need K * sizeof(value) in {64, 128, 256}
- * bytes and 16-byte aligned dense rows; C / out are written exactly like the _csr entry points. */
+ * bytes and 16-byte aligned dense rows; `out` of the SDDMM is written exactly like tsgu_sddmm_csr; the SpMM writes element
+ * (r, k) of item t at C + t*c_bs + r*ldc + k*c_cs: c_cs == 1 is the row-major result of tsgu_spmm_csr, ldc == 1 a
+ * column-major one (grad_B in the layout of a column-major B, without a separate layout pass). */
 TSGU_API int tsgu_window_limits(int* tile_rows_max, int* entries_max, int* window_rows, int* runs_max);
 TSGU_API int tsgu_window_plan(const void* rowptr, const void* colind, int64_t batch, int64_t n,
                      int64_t rowptr_bstride, int64_t nnz_bstride, int idx_dtype, int tile_rows,
@@ -257,8 +259,8 @@ TSGU_API int tsgu_window_plan(const void* rowptr, const void* colind, int64_t ba
 TSGU_API int tsgu_spmm_window(const void* rowptr, const void* lcol, const void* desc, const void* vals,
                      const void* perm, const void* B, void* C, int64_t batch, int64_t n, int64_t K,
                      int64_t rowptr_bstride, int64_t nnz_bstride, int64_t nnz_len, int tile_rows,
-                     int64_t b_bs, int64_t b_rs, int64_t c_bs, int64_t ldc, int val_dtype, int idx_dtype,
-                     void* stream);
+                     int64_t b_bs, int64_t b_rs, int64_t c_bs, int64_t ldc, int64_t c_cs, int val_dtype,
+                     int idx_dtype, void* stream);
 TSGU_API int tsgu_sddmm_window(const void* rowptr, const void* lcol, const void* desc, const void* out_index,
                       const void* G, const void* B, void* out, int64_t batch, int64_t n, int64_t K,
                       int64_t rowptr_bstride, int64_t nnz_bstride, int64_t nnz_len, int tile_rows,

@@ -128,6 +128,29 @@ def test_stencil_window_column_major_B():
     _check_against_oracle(A, 32, torch.float32, b_colmajor=True)
 
 
+@pytest.mark.parametrize("D,K,dtype", [(15, 32, torch.float32), (13, 16, torch.float32), (12, 64, torch.float32),
+                                       (14, 64, torch.bfloat16), (11, 32, torch.bfloat16)])
+def test_column_major_epilogue_shapes(D, K, dtype):
+    """grad_B is written column-major by the SpMM's transposing epilogue: row counts that are not multiples of the
+    rows per warp / per tile, 4- and 8-lane groups, 64 / 128 / 256-byte rows, fp32 and bf16."""
+    from torchsparsegradutils_b200 import sparse_mm
+
+    A = W.stencil27_csr(D, dtype, torch.int32, DEV, seed=3)
+    _check_against_oracle(A, K, dtype, b_colmajor=True)
+    n = A.shape[0]
+    B = torch.rand(K, n, device=DEV).to(dtype).t().requires_grad_(True)  # column-major leaf
+    C = sparse_mm(A, B)
+    C.backward(torch.rand(n, K, device=DEV).to(dtype))
+    assert B.grad.stride() == B.stride()
+
+
+def test_batched_column_major_epilogue():
+    As = [W.stencil27_csr(11, torch.float32, torch.int32, DEV, seed=s) for s in (1, 2)]
+    A = torch.sparse_csr_tensor(torch.stack([a.crow_indices() for a in As]), torch.stack([a.col_indices() for a in As]),
+                                torch.stack([a.values() for a in As]), (2,) + tuple(As[0].shape))
+    _check_against_oracle(A, 32, torch.float32, b_colmajor=True)
+
+
 def test_lower_triangular_stencil_window():
     A = W.stencil27_csr(18, torch.float32, torch.int32, DEV, seed=3, lower=True)
     _check_against_oracle(A, 32, torch.float32)

@@ -217,10 +217,14 @@ def _window_for(pat: CsrPattern, algo: int, *dense: torch.Tensor) -> Optional[Wi
 
 
 def _spmm_window(pat: CsrPattern, wp: WindowPlan, vals: torch.Tensor, dense: torch.Tensor, tag: str,
-                 vals_in_pattern_order: bool) -> torch.Tensor:
+                 vals_in_pattern_order: bool, out_strides=None) -> torch.Tensor:
     dev = dense.device
     K = dense.shape[-1]
-    out = torch.empty((pat.batch, pat.n, K), dtype=dense.dtype, device=dev)
+    colmajor = out_strides is not None and tuple(out_strides) == (pat.n * K, 1, pat.n) and K > 1 and pat.n > 1
+    if colmajor:  # every item column-major: written directly by the kernel's transposing epilogue
+        out = torch.empty_strided((pat.batch, pat.n, K), (pat.n * K, 1, pat.n), dtype=dense.dtype, device=dev)
+    else:
+        out = torch.empty((pat.batch, pat.n, K), dtype=dense.dtype, device=dev)
     perm = None if vals_in_pattern_order else pat.perm
     if perm is not None and not _WINDOW_PERM_IN_KERNEL:
         with _timer(tag + "_gather", dev):
@@ -231,15 +235,19 @@ def _spmm_window(pat: CsrPattern, wp: WindowPlan, vals: torch.Tensor, dense: tor
         nat.check(nat.lib().tsgu_spmm_window(nat.ptr(pat.rowptr), nat.ptr(wp.lcol), nat.ptr(wp.desc), nat.ptr(vals),
                                              nat.ptr(perm), dense.data_ptr(), out.data_ptr(), pat.batch, pat.n, K,
                                              pat.rowptr_bstride, pat.nnz_bstride, pat.colind.numel(), wp.tile_rows,
-                                             bs, rs if pat.m > 1 else K, pat.n * K, K, nat.val_enum(dense.dtype), pat.idx,
+                                             bs, rs if pat.m > 1 else K, pat.n * K, 1 if colmajor else K,
+                                             pat.n if colmajor else 1, nat.val_enum(dense.dtype), pat.idx,
                                              nat.stream_ptr(dev)), "tsgu_spmm_window")
     return out
 
 
 def spmm(pat: CsrPattern, vals: torch.Tensor, dense: torch.Tensor, algo: Optional[int] = None,
-         tag: str = "spmm", vals_in_pattern_order: bool = False) -> torch.Tensor:
+         tag: str = "spmm", vals_in_pattern_order: bool = False, out_strides=None) -> torch.Tensor:
     """out[t] = A[t] @ dense[t]; dense is (batch, m, K) (any strides); returns contiguous (batch, n, K).
-    `vals_in_pattern_order`: `vals` were already gathered through `pat.perm` by the caller (gather_values)."""
+    `vals_in_pattern_order`: `vals` were already gathered through `pat.perm` by the caller (gather_values).
+    `out_strides`: a layout the caller would like the (batch, n, K) result in; honoured where a kernel can write it
+    directly (column-major items from the column-window kernels), otherwise the result is contiguous and the caller
+    re-strides it."""
     algo = pat.algo if algo is None else algo
     if algo == nat.ALGO_SPLIT:
         d3 = prepare_dense(_as3d(dense))
@@ -251,7 +259,7 @@ def spmm(pat: CsrPattern, vals: torch.Tensor, dense: torch.Tensor, algo: Optiona
     if pat.batch * pat.n * K and pat.nnz_total:
         wp = _window_for(pat, algo, dense)
         if wp is not None:
-            return _spmm_window(pat, wp, vals, dense, tag, vals_in_pattern_order)
+            return _spmm_window(pat, wp, vals, dense, tag, vals_in_pattern_order, out_strides)
     out = torch.empty((pat.batch, pat.n, K), dtype=dense.dtype, device=dense.device)
     if out.numel() == 0:
         return out

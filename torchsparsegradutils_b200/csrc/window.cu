@@ -235,6 +235,8 @@ template <typename V, typename I, int ROWB, bool PERM, bool GROWS = false>
 struct WinSmem {
   WinStage<V, I, ROWB, PERM, GROWS> st[TSGU_WIN_STAGES];
   WinInfoRing<I> ring;
+  // SpMM with a column-major result: per-warp scratch for the (rows of a warp) x K transpose (16-byte padded rows)
+  alignas(16) unsigned char cscr[GROWS ? 16 : TSGU_WIN_CW * 8 * (ROWB + 16)];
   alignas(8) uint64_t full[TSGU_WIN_STAGES];
   alignas(8) uint64_t empty[TSGU_WIN_STAGES];
 };
@@ -253,6 +255,7 @@ struct WinParams {
   int64_t batch, n;
   int64_t rowptr_bstride, nnz_bstride, rowptr_len, nnz_len;
   int64_t b_bs, b_rs, g_bs, g_rs, c_bs, ldc;
+  int64_t c_cs;  // SpMM result: element (r, k) of an item at r * ldc + k * c_cs; c_cs == 1 row-major, ldc == 1 column-major
   int64_t tiles_per_item, num_tiles;
   int tile_rows;
 };
@@ -457,9 +460,11 @@ __global__ void __launch_bounds__(TSGU_WIN_CW * 32 + 32) spmm_window_kernel(cons
     const int al4 = s_al - s_rel;  // (e + al4) & 3 == 0  <=>  entry e is 4-aligned in both staged arrays
     const I* sprm = st.prm + (s_al & (AI - 1)) - s_rel;
 
-    for (int lr = group; lr < rows; lr += GROUPS) {
-      const int e0 = (int)st.rp[rp_shift + lr];
-      const int e1 = (int)st.rp[rp_shift + lr + 1];
+    for (int lr0 = 0; lr0 < rows; lr0 += GROUPS) {  // warp-uniform trip count; a group past the tile's end idles
+      const int lr = lr0 + group;
+      const bool active = lr < rows;
+      const int e0 = active ? (int)st.rp[rp_shift + lr] : 0;
+      const int e1 = active ? (int)st.rp[rp_shift + lr + 1] : 0;
       Acc acc[VPL][EPV];
 #pragma unroll
       for (int w = 0; w < VPL; ++w)
@@ -555,9 +560,41 @@ __global__ void __launch_bounds__(TSGU_WIN_CW * 32 + 32) spmm_window_kernel(cons
           }
         }
       }
-      V* Crow = p.out + (int64_t)ti.item * p.c_bs + (int64_t)(r0 + lr) * p.ldc;
+      if (p.c_cs == 1) {  // row-major result: one 128-bit store per vector
+        if (active) {
+          V* Crow = p.out + (int64_t)ti.item * p.c_bs + (int64_t)(r0 + lr) * p.ldc;
 #pragma unroll
-      for (int w = 0; w < VPL; ++w) store_vec<V, EPV>(Crow + (w * LPR + gl) * EPV, acc[w]);
+          for (int w = 0; w < VPL; ++w) store_vec<V, EPV>(Crow + (w * LPR + gl) * EPV, acc[w]);
+        }
+      } else {
+        // column-major result (grad_B handed back in the layout of a column-major B): the R = 32 / LPR rows of this
+        // warp are consecutive, so after a transpose through shared memory lane k owns R consecutive elements of
+        // column k -- one 16-byte (fp32) / 8-byte (bf16) store instead of a separate layout pass over the result
+        constexpr int R = 32 / LPR, KE = ROWB / (int)sizeof(V), PITCH = KE + 16 / (int)sizeof(V);
+        V* scr = reinterpret_cast<V*>(sm.cscr) + warp * (8 * PITCH);
+        const int g_in_warp = lane / LPR;
+#pragma unroll
+        for (int w = 0; w < VPL; ++w) store_vec<V, EPV>(scr + g_in_warp * PITCH + (w * LPR + gl) * EPV, acc[w]);
+        __syncwarp();
+        const int row0 = r0 + lr0 + warp * R;         // first row of this warp in this pass
+        const int valid = rows - (lr0 + warp * R);    // rows of the warp inside the tile (may be <= 0)
+        V* Cit = p.out + (int64_t)ti.item * p.c_bs;
+        for (int k = lane; k < KE; k += 32) {
+          V* dst = Cit + (int64_t)k * p.c_cs + (int64_t)row0 * p.ldc;
+          struct alignas(R * sizeof(V)) Pack { V x[R]; };
+          Pack pk;
+#pragma unroll
+          for (int j = 0; j < R; ++j) pk.x[j] = scr[j * PITCH + k];
+          if (valid >= R && p.ldc == 1 && (reinterpret_cast<uintptr_t>(dst) % (R * sizeof(V))) == 0) {
+            *reinterpret_cast<Pack*>(dst) = pk;
+          } else {
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+              if (j < valid) dst[(int64_t)j * p.ldc] = pk.x[j];
+          }
+        }
+        __syncwarp();
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[s]);  // this warp is done reading the stage
@@ -747,7 +784,7 @@ template <typename V, typename I>
 static int window_run(bool sddmm, const void* rowptr, const void* lcol, const void* desc, const void* vals, const void* perm,
                       const void* out_index, const void* G, const void* B, void* out, int64_t batch, int64_t n, int64_t K,
                       int64_t rowptr_bstride, int64_t nnz_bstride, int64_t nnz_len, int tile_rows, int64_t g_bs, int64_t g_rs,
-                      int64_t b_bs, int64_t b_rs, int64_t c_bs, int64_t ldc, cudaStream_t s) {
+                      int64_t b_bs, int64_t b_rs, int64_t c_bs, int64_t ldc, int64_t c_cs, cudaStream_t s) {
   constexpr int EPV = 16 / (int)sizeof(V);
   WinParams<V, I> p;
   p.rowptr = (const I*)rowptr; p.lcol = (const uint16_t*)lcol; p.desc = (const int32_t*)desc;
@@ -756,14 +793,14 @@ static int window_run(bool sddmm, const void* rowptr, const void* lcol, const vo
   p.batch = batch; p.n = n; p.rowptr_bstride = rowptr_bstride; p.nnz_bstride = nnz_bstride;
   p.rowptr_len = nnz_bstride > 0 ? batch * rowptr_bstride : batch * n + 1;
   p.nnz_len = nnz_len;
-  p.b_bs = b_bs; p.b_rs = b_rs; p.g_bs = g_bs; p.g_rs = g_rs; p.c_bs = c_bs; p.ldc = ldc;
+  p.b_bs = b_bs; p.b_rs = b_rs; p.g_bs = g_bs; p.g_rs = g_rs; p.c_bs = c_bs; p.ldc = ldc; p.c_cs = c_cs;
   p.tile_rows = tile_rows;
   p.tiles_per_item = (n + tile_rows - 1) / tile_rows;
   p.num_tiles = p.tiles_per_item * batch;
   const bool ok = (b_rs % EPV) == 0 && (b_bs % EPV) == 0 && aligned16(B) && aligned16(rowptr) && aligned16(lcol) &&
                   aligned16(vals) && aligned16(perm) &&
                   (sddmm ? ((g_rs % EPV) == 0 && (g_bs % EPV) == 0 && aligned16(G))
-                         : ((ldc % EPV) == 0 && (c_bs % EPV) == 0 && aligned16(out)));
+                         : (c_cs == 1 ? ((ldc % EPV) == 0 && (c_bs % EPV) == 0 && aligned16(out)) : true));
   if (!ok) return TSGU_ERR_SHAPE;
   return window_dispatch<V, I>(p, K, sddmm, s);
 }
@@ -779,11 +816,11 @@ static int window_run(bool sddmm, const void* rowptr, const void* lcol, const vo
 extern "C" int tsgu_spmm_window(const void* rowptr, const void* lcol, const void* desc, const void* vals, const void* perm,
                                 const void* B, void* C, int64_t batch, int64_t n, int64_t K, int64_t rowptr_bstride,
                                 int64_t nnz_bstride, int64_t nnz_len, int tile_rows, int64_t b_bs, int64_t b_rs, int64_t c_bs,
-                                int64_t ldc, int val_dtype, int idx_dtype, void* stream) {
+                                int64_t ldc, int64_t c_cs, int val_dtype, int idx_dtype, void* stream) {
   if (batch < 0 || n < 0 || K <= 0 || tile_rows < 1 || tile_rows > TSGU_WIN_TMAX) return TSGU_ERR_SHAPE;
   if (batch == 0 || n == 0) return 0;
   TSGU_WIN_DISPATCH(window_run<V, I>(false, rowptr, lcol, desc, vals, perm, nullptr, nullptr, B, C, batch, n, K, rowptr_bstride,
-                                     nnz_bstride, nnz_len, tile_rows, 0, 0, b_bs, b_rs, c_bs, ldc, as_stream(stream)));
+                                     nnz_bstride, nnz_len, tile_rows, 0, 0, b_bs, b_rs, c_bs, ldc, c_cs, as_stream(stream)));
 }
 
 extern "C" int tsgu_sddmm_window(const void* rowptr, const void* lcol, const void* desc, const void* out_index, const void* G,
@@ -793,6 +830,6 @@ extern "C" int tsgu_sddmm_window(const void* rowptr, const void* lcol, const voi
   if (batch < 0 || n < 0 || K <= 0 || tile_rows < 1 || tile_rows > TSGU_WIN_TMAX) return TSGU_ERR_SHAPE;
   if (batch == 0 || n == 0 || nnz_len == 0) return 0;
   TSGU_WIN_DISPATCH(window_run<V, I>(true, rowptr, lcol, desc, nullptr, nullptr, out_index, G, B, out, batch, n, K,
-                                     rowptr_bstride, nnz_bstride, nnz_len, tile_rows, g_bs, g_rs, b_bs, b_rs, 0, 0,
+                                     rowptr_bstride, nnz_bstride, nnz_len, tile_rows, g_bs, g_rs, b_bs, b_rs, 0, 0, 1,
                                      as_stream(stream)));
 }

@@ -189,8 +189,11 @@ def _grad_B(ctx, grad):
         vals = aligned_contiguous(A.values())
     else:
         vals = aligned_contiguous(A._values())
-    gradB = _ops.spmm(csr.transpose(), vals, grad, tag="spmm_gradB")
+    want = None
+    if ctx.B_strides is not None:  # ask for B's own layout; kernels that can write it directly save the re-stride pass
+        want = tuple(ctx.B_strides) if ctx.batched else (ctx.B_shape[0] * ctx.B_shape[1],) + tuple(ctx.B_strides)
+    gradB = _ops.spmm(csr.transpose(), vals, grad, tag="spmm_gradB", out_strides=want)
     gradB = gradB if ctx.batched else gradB[0]
-    if ctx.B_strides is not None:
+    if ctx.B_strides is not None and tuple(gradB.stride()) != tuple(ctx.B_strides):
         gradB = _ops.restride_like(gradB, ctx.B_shape, ctx.B_strides)
     return gradB
