@@ -322,7 +322,7 @@ def _build_transpose(p: CsrPattern) -> CsrPattern:
         permT = p.perm.to(odt).index_select(0, permT.long()) if p.perm.dtype != odt else p.perm.index_select(0, permT.long())
     algo = choose_algo(rowptrT, p.batch, p.m, p.nnz_total)
     nnzT = p.nnz_total
-    patT = CsrPattern(rowptrT, colindT, permT, p.batch, p.m, p.n, p.m, 0, nnzT, out_idx, algo=algo, keep=(p,))
+    patT = CsrPattern(rowptrT, colindT, permT, p.batch, p.m, p.n, p.m, 0, nnzT, out_idx, algo=algo)
     if algo == nat.ALGO_AUTO and nnzT >= _PAD_MIN_NNZ and window_plan(patT) is None:
         # no column-window structure: the row-tile kernels take it.  Two layout optimisations of a structure WE own:
         # rows sorted by length inside every item (the 4 rows a warp works on together then hold the same number of
@@ -333,7 +333,7 @@ def _build_transpose(p: CsrPattern) -> CsrPattern:
             rowptrT, colindT, permT, row_map = _sort_rows_by_length(rowptrT, colindT, permT, p.batch, p.m)
         if out_idx == nat.I64 or nnzT + (_ROW_PAD - 1) * p.batch * p.m < _I32_MAX:
             rowptrT, colindT, permT, nnzT = _pad_rows(rowptrT, colindT, permT, _ROW_PAD)
-        patT = CsrPattern(rowptrT, colindT, permT, p.batch, p.m, p.n, p.m, 0, nnzT, out_idx, algo=algo, keep=(p,),
+        patT = CsrPattern(rowptrT, colindT, permT, p.batch, p.m, p.n, p.m, 0, nnzT, out_idx, algo=algo,
                           row_map=row_map)
     return _with_split(patT)
 
