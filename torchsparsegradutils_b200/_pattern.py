@@ -139,6 +139,7 @@ class CsrPattern:
     split: Optional["SplitRows"] = None  # virtual-row view of a skewed pattern (algo == ALGO_SPLIT)
     keep: tuple = ()  # tensors whose storage must outlive this pattern (cache-key owners)
     row_map: Optional[torch.Tensor] = None  # rows were permuted: CSR row s of item t is output row row_map[t*n + s]
+    padded: bool = False  # perm holds -1 entries (explicit zeros): the values MUST go through gather_values, never the in-kernel perm path
     extras: dict = field(default_factory=dict, repr=False)  # per-pattern plans built lazily by _ops (window plans, ...)
     fingerprint: Optional[torch.Tensor] = field(default=None, repr=False)
     cache_key: Optional[tuple] = field(default=None, repr=False)
@@ -334,7 +335,7 @@ def _build_transpose(p: CsrPattern) -> CsrPattern:
         if out_idx == nat.I64 or nnzT + (_ROW_PAD - 1) * p.batch * p.m < _I32_MAX:
             rowptrT, colindT, permT, nnzT = _pad_rows(rowptrT, colindT, permT, _ROW_PAD)
         patT = CsrPattern(rowptrT, colindT, permT, p.batch, p.m, p.n, p.m, 0, nnzT, out_idx, algo=algo,
-                          row_map=row_map)
+                          row_map=row_map, padded=nnzT > p.nnz_total)
     return _with_split(patT)
 
 
