@@ -212,3 +212,69 @@ def test_bench_stdout_carries_only_the_json_line(tmp_path):
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1 and json.loads(lines[0]) == {"metric": "m", "value": 1}
     assert "NCCL version banner" in r.stderr and "python-level chatter" in r.stderr
+
+
+def test_sort_rows_by_length_is_a_row_permutation_with_snake_blocks():
+    """Host-side layout optimisation of the cached transpose (pure index arithmetic, runs on any device): rows are
+    permuted inside blocks of 64, alternately longest-first / shortest-first, entries of a row stay together and in
+    order, and row_map sends every slot back to its original row."""
+    import torch
+
+    from torchsparsegradutils_b200 import _pattern as P
+
+    g = torch.Generator().manual_seed(0)
+    batch, rows = 2, 200
+    lens = torch.randint(0, 9, (batch * rows,), generator=g)
+    rowptr = torch.zeros(batch * rows + 1, dtype=torch.int32)
+    rowptr[1:] = lens.cumsum(0)
+    nnz = int(rowptr[-1])
+    col = torch.randint(0, 50, (nnz,), generator=g, dtype=torch.int32)
+    perm = torch.randperm(nnz, generator=g).to(torch.int32)
+    rp2, col2, perm2, row_map = P._sort_rows_by_length(rowptr, col, perm, batch, rows)
+    assert rp2.dtype == rowptr.dtype and int(rp2[-1]) == nnz and row_map.numel() == batch * rows
+    new_lens = (rp2[1:] - rp2[:-1]).long()
+    for t in range(batch):
+        rm = row_map[t * rows:(t + 1) * rows].long()
+        assert torch.equal(rm.sort().values, torch.arange(rows))  # a permutation inside every item
+        for s in range(rows):
+            o = t * rows + int(rm[s])
+            a, b = int(rowptr[o]), int(rowptr[o + 1])
+            a2, b2 = int(rp2[t * rows + s]), int(rp2[t * rows + s + 1])
+            assert torch.equal(col2[a2:b2], col[a:b]) and torch.equal(perm2[a2:b2], perm[a:b])
+        blocks = new_lens[t * rows:(t + 1) * rows].split(P._SORT_BLOCK)
+        for k, blk in enumerate(blocks):
+            d = blk[1:] - blk[:-1]
+            assert bool((d <= 0).all()) if k % 2 == 0 else bool((d >= 0).all())
+            # block membership is unchanged: a block holds the rows it held before
+            lo = k * P._SORT_BLOCK
+            assert set(row_map[t * rows + lo: t * rows + lo + blk.numel()].tolist()) == set(range(lo, lo + blk.numel()))
+
+
+def test_bench_config_is_identical_for_both_arms_and_deterministic():
+    import argparse
+    import sys, os
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    for cid in ("2", "3", "4", "5"):
+        for world in (1, 2, 8):
+            a = argparse.Namespace(config=cid, scaling="strong", sharding="k", grad_b="all_reduce", no_overlap=False)
+            c1 = bench.describe_config(bench.CONFIGS[cid], a, world)
+            c2 = bench.describe_config(bench.CONFIGS[cid], a, world)
+            assert c1 == c2 and set(c1[0]) == {"workload", "config_id", "K", "l2", "sharding"}
+    # strong scaling of the batched config: per-rank footprint shrinks with the ranks, flush policy follows
+    a = argparse.Namespace(config="2", scaling="strong", sharding="k", grad_b="all_reduce", no_overlap=False)
+    assert bench.describe_config(bench.CONFIGS["2"], a, 1)[3] is False and bench.describe_config(bench.CONFIGS["2"], a, 8)[3] is True
+
+
+def test_aligned_contiguous_copies_only_misaligned_views():
+    import torch
+
+    from torchsparsegradutils_b200._pattern import aligned_contiguous
+
+    base = torch.arange(64, dtype=torch.int32)
+    assert aligned_contiguous(base) is base
+    v = base[1:33]
+    c = aligned_contiguous(v)
+    assert c is not v and c.data_ptr() % 16 == 0 and torch.equal(c, v)
