@@ -319,7 +319,10 @@ __global__ void __launch_bounds__(256, TSGU_TILE_MINB(VPL)) sddmm_tile_kernel(co
 template <typename V, typename I, int LPR, int VPL>
 static int launch_sddmm_tile(const SddmmParams<V, I>& p, int64_t nnz_total, cudaStream_t s) {
   using Cfg = TileCfg<V, I, 0>;
-  constexpr int NB = 16;  // entries per batch (butterfly leaves NB/LPR results per lane when NB > LPR)
+#ifndef TSGU_SDDMM_NB
+#define TSGU_SDDMM_NB 8   // swept on the box: 8 -> no spills at the 128-register cap (config 2 SDDMM 0.282 -> 0.264 ms), 16: 24 B of spills, 32: 0.325 ms
+#endif
+  constexpr int NB = TSGU_SDDMM_NB;  // entries per batch (butterfly leaves NB/LPR results per lane when NB > LPR)
   constexpr int U0 = TSGU_TILE_LOADS(VPL) / VPL;
   constexpr int U = U0 < NB ? U0 : NB;
   constexpr int EPV = 16 / sizeof(V);
