@@ -653,40 +653,64 @@ def run_e2e(A, B, G, steps, dev, dist, sparse_mm):
     item_shape = tuple(A.shape[1:]) if batched else tuple(A.shape)
     sl = (lambda t, i: t[i]) if batched else (lambda t, i: t)
     s_in, s_cmp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    NSLOT = 3
+    NSLOT = int(os.environ.get("TSGU_E2E_SLOTS", "4"))
+    LOOKAHEAD = NSLOT - 1  # items whose H2D is queued ahead of the one being enqueued for compute: the host blocks in the
+                           # pattern builds (host syncs), PCIe must not run dry meanwhile
     slots = [dict(A=[torch.empty_like(sl(t, 0), device=dev) for t in hA], B=torch.empty_like(sl(hB, 0), device=dev),
                   G=torch.empty_like(sl(hG, 0), device=dev), free=torch.cuda.Event()) for _ in range(NSLOT)]
 
+    from torchsparsegradutils_b200 import clear_pattern_cache, prepare_pattern
+
+    # diagnostics only (scripts/e2e_probe.py): where the host's time goes, and two what-if switches
+    trace = {"prepare": 0.0, "enqueue": 0.0, "d2h": 0.0, "wait": 0.0} if os.environ.get("TSGU_E2E_TRACE") else None
+    what_if_warm = os.environ.get("TSGU_E2E_WHATIF_WARM") == "1"      # keep the (stale) cached patterns: the r1 behaviour
+    what_if_no_d2h = os.environ.get("TSGU_E2E_WHATIF_NO_D2H") == "1"  # skip the result copies
+
+    def make_A(slot):
+        if is_csr:
+            return torch.sparse_csr_tensor(slot["A"][0], slot["A"][1], slot["A"][2], item_shape)
+        return torch.sparse_coo_tensor(slot["A"][0], slot["A"][1], item_shape, is_coalesced=True)
+
     def upload(i):
+        """H2D of item i: the sparse operand first, then the dense ones; returns (A is on the device, all is)."""
         slot = slots[i % NSLOT]
-        ev_in = torch.cuda.Event()
+        ev_A, ev_in = torch.cuda.Event(), torch.cuda.Event()
         with torch.cuda.stream(s_in):
             s_in.wait_event(slot["free"])  # the compute that last used this slot is done
             for d, h in zip(slot["A"], hA):
                 d.copy_(sl(h, i), non_blocking=True)
+            ev_A.record(s_in)
             slot["B"].copy_(sl(hB, i), non_blocking=True)
             slot["G"].copy_(sl(hG, i), non_blocking=True)
             ev_in.record(s_in)
-        return ev_in
+        return ev_A, ev_in
 
     inflight = collections.deque()  # (all results of the step are in host memory, tensors its D2H still reads)
 
     def one_step():
         keep = []
-        ev_next = upload(0)
+        pending = collections.deque(upload(j) for j in range(min(LOOKAHEAD, items)))
         for i in range(items):
             slot = slots[i % NSLOT]
-            ev_in, ev_cmp = ev_next, torch.cuda.Event()
-            if i + 1 < items:  # queue the next upload before this item's (host-synchronising) pattern build
-                ev_next = upload(i + 1)
+            if i + LOOKAHEAD < items:
+                pending.append(upload(i + LOOKAHEAD))
+            (ev_A, ev_in), ev_cmp = pending.popleft(), torch.cuda.Event()
             with torch.cuda.stream(s_cmp):
+                # the pattern-only work (transpose, plans) starts as soon as A's index arrays are on the device, while
+                # the dense operands of this item are still crossing PCIe
+                s_cmp.wait_event(ev_A)
+                # a data loader delivers a NEW matrix into this device slot: its pattern is not the cached one.  The slot's
+                # index buffers were rewritten in place (which the cache key cannot see), so the cache is dropped here and
+                # every item of every step pays its pattern build inside the timed region.
+                t_a = time.perf_counter()
+                if not what_if_warm:
+                    clear_pattern_cache()
+                As = make_A(slot).requires_grad_(True)
+                prepare_pattern(As, reuse=False)  # this matrix lives for one step
+                t_b = time.perf_counter()
                 s_cmp.wait_event(ev_in)
                 dB = slot["B"].requires_grad_(True)
                 dB.grad = None
-                if is_csr:
-                    As = torch.sparse_csr_tensor(slot["A"][0], slot["A"][1], slot["A"][2], item_shape).requires_grad_(True)
-                else:
-                    As = torch.sparse_coo_tensor(slot["A"][0], slot["A"][1], item_shape, is_coalesced=True).requires_grad_(True)
                 C = sparse_mm(As, dB)
                 C.backward(slot["G"])
                 gv = As.grad.values() if is_csr else As.grad._values()
@@ -694,19 +718,28 @@ def run_e2e(A, B, G, steps, dev, dist, sparse_mm):
                 dB.requires_grad_(False)
                 ev_cmp.record(s_cmp)
                 slot["free"].record(s_cmp)
+            t_c = time.perf_counter()
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_cmp)
-                sl(outC, i).copy_(C.detach(), non_blocking=True)
-                sl(outgB, i).copy_(gB, non_blocking=True)
-                sl(outgA, i).copy_(gv.reshape(sl(outgA, i).shape), non_blocking=True)
+                if not what_if_no_d2h:
+                    sl(outC, i).copy_(C.detach(), non_blocking=True)
+                    sl(outgB, i).copy_(gB, non_blocking=True)
+                    sl(outgA, i).copy_(gv.reshape(sl(outgA, i).shape), non_blocking=True)
+            if trace is not None:
+                trace["prepare"] += t_b - t_a
+                trace["enqueue"] += t_c - t_b
+                trace["d2h"] += time.perf_counter() - t_c
             keep.append((C, gB, gv, As))  # outputs live until their D2H is done
         ev_done = torch.cuda.Event()
         ev_done.record(s_out)
         inflight.append((ev_done, keep))
+        t_w = time.perf_counter()
         while len(inflight) > 1:  # two steps in flight at most: the older one's results must have landed
             ev, k = inflight.popleft()
             ev.synchronize()
             k.clear()
+        if trace is not None:
+            trace["wait"] += time.perf_counter() - t_w
 
     def drain():
         while inflight:
@@ -720,19 +753,35 @@ def run_e2e(A, B, G, steps, dev, dist, sparse_mm):
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
+    if trace is not None:
+        trace.update(dict.fromkeys(trace, 0.0))
     t0 = time.perf_counter()
     for _ in range(steps):
         one_step()
     drain()
     torch.cuda.synchronize()
     ms = (time.perf_counter() - t0) * 1e3 / steps  # host wall clock; every step's copies and results inside
+    if trace is not None:
+        print("e2e host ms/step:", {k: round(v * 1e3 / steps, 3) for k, v in trace.items()}, "total", round(ms, 3),
+              file=sys.stderr)
+    # what landed in host memory is the op's result (outside the timed region): compare with a device-resident run
+    clear_pattern_cache()
+    Ad = A.detach().requires_grad_(True)
+    Bd = B.detach().requires_grad_(True)
+    Cd = sparse_mm(Ad, Bd)
+    Cd.backward(G)
+    gAd = Ad.grad.values() if is_csr else Ad.grad._values()
+    tol = dict(rtol=2e-2, atol=2e-2) if B.dtype == torch.bfloat16 else dict(rtol=1e-4, atol=1e-3)
+    verified = bool(torch.allclose(outC.to(dev), Cd.detach(), **tol) and torch.allclose(outgB.to(dev), Bd.grad, **tol)
+                    and torch.allclose(outgA.to(dev).reshape(-1), gAd.reshape(-1), **tol))
     if dist is not None:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
     return {"value": None, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms,
-            "ms_per_step_max": ms, "steps": steps, "pipeline": f"{items} item(s) on 3 streams (H2D | fwd+bwd | D2H), 2 steps in flight",
-            "note": "pattern cache cold every step (index tensors rewritten): includes the CSR transpose build"}
+            "ms_per_step_max": ms, "steps": steps, "results_verified": verified, "pipeline": f"{items} item(s) on 3 streams (H2D | fwd+bwd | D2H), H2D queued {LOOKAHEAD} items ahead, 2 steps in flight",
+            "note": "pattern cache cold every step (index tensors rewritten): the CSR transpose / plan builds are inside the timed "
+                    "region, issued (prepare_pattern) as soon as A's arrays have arrived, under the H2D of the dense operands"}
 
 
 if __name__ == "__main__":

@@ -75,6 +75,15 @@ TSGU_API int64_t tsgu_launch_count(void);
  * grad_B reduction overlapped with the SDDMM): a persistent grid that owns every SM would otherwise
  * keep NCCL's kernels waiting until it drains. */
 TSGU_API int tsgu_set_sm_margin(int sms);
+/* Host mailbox: `bytes` of mapped pinned host memory (host_ptr for the host to read, dev_ptr for kernels to write) and
+ * tsgu_publish(), a one-block kernel that stores `bytes` (multiple of 4) of device memory `src` into a mailbox on
+ * `stream`.  Synchronise the stream, then read host_ptr.  This is how the host side learns the few scalars a new
+ * sparsity pattern produces (longest row, window-plan verdict, padded size -- the reference gets the same facts from
+ * `.item()`-style reads inside torch.sparse.mm's planning): unlike a cudaMemcpy the store does not queue behind bulk
+ * D2H transfers on the copy engines. */
+TSGU_API int tsgu_mailbox_create(size_t bytes, void** host_ptr, void** dev_ptr);
+TSGU_API int tsgu_mailbox_destroy(void* host_ptr);
+TSGU_API int tsgu_publish(const void* src, void* mailbox_dev, size_t bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * SpMM:  C[t] = A[t] * B[t]                 replaces torch.sparse.mm(A, B)

@@ -20,6 +20,7 @@ SEED = 42
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "default_layout_policy: keep the product's default (layout optimised on the 2nd use)")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -38,6 +39,18 @@ def _seed_everything():
     torch.manual_seed(SEED)
     if torch.cuda.is_available():
         torch.cuda.manual_seed_all(SEED)
+    yield
+
+
+@pytest.fixture(autouse=True)
+def _optimised_layout_from_first_use(request, monkeypatch):
+    """The cached transpose gets its layout optimisations (rows sorted in blocks, padded) on the SECOND use by default;
+    most tests run one forward + backward per pattern, so they switch to "from the first use" to keep exercising the
+    sorted / padded kernels paths.  Tests marked `default_layout_policy` cover the default."""
+    if "default_layout_policy" not in request.keywords:
+        from torchsparsegradutils_b200 import _pattern
+
+        monkeypatch.setattr(_pattern, "_LAYOUT_AFTER_USES", 1)
     yield
 
 

@@ -128,6 +128,41 @@ def test_config2_transpose_structure_full_size(monkeypatch):
     assert torch.equal(TT.perm.long(), torch.arange(nnz, device=DEV))
 
 
+@pytest.mark.default_layout_policy
+def test_transposed_layout_is_optimised_on_the_second_use():
+    """Default policy: the first backward runs on the plain transposed CSR (a pattern used once does not pay the
+    block sort + padding), the second one upgrades it; the gradients do not change by a bit, and the mailbox host read
+    the builds rely on returns what .tolist() would."""
+    import torchsparsegradutils_b200 as tsgu
+    from torchsparsegradutils_b200 import _native as nat
+    from torchsparsegradutils_b200._pattern import csr_pattern
+
+    probe = torch.tensor([3, -1, 2**40, 0], device=DEV)
+    assert nat.host_read(probe) == probe.tolist() and nat.host_read(probe.int()[:2]) == [3, -1]
+    tsgu.clear_pattern_cache()
+    A = W.uniform_rows_csr(2, 65536, 65536, 16, torch.float32, torch.int32, DEV, seed=17)
+    B, G = W.dense_operands((2, 65536, 65536), 64, torch.float32, DEV, seed=18)
+    nnz = 2 * 65536 * 16
+    C1, gA1, gB1 = _fwd_bwd(A, B, G)
+    T1 = csr_pattern(A)._transpose
+    assert T1 is not None and T1.row_map is None and not T1.padded and T1.nnz_total == nnz
+    C2, gA2, gB2 = _fwd_bwd(A, B, G)
+    T2 = csr_pattern(A)._transpose
+    assert T2 is not T1 and T2.row_map is not None and T2.padded and T2.nnz_total > nnz
+    C3, gA3, gB3 = _fwd_bwd(A, B, G)
+    assert csr_pattern(A)._transpose is T2
+    for x, y, z in ((C1, C2, C3), (gA1.values(), gA2.values(), gA3.values()), (gB1, gB2, gB3)):
+        assert torch.equal(x, y) and torch.equal(y, z)
+    # a one-step pattern announced as such stays plain; an announced long-lived one is optimised up front
+    tsgu.clear_pattern_cache()
+    tsgu.prepare_pattern(A, reuse=False)
+    assert not csr_pattern(A)._transpose.padded
+    tsgu.clear_pattern_cache()
+    tsgu.prepare_pattern(A)
+    assert csr_pattern(A)._transpose.padded
+    tsgu.clear_pattern_cache()
+
+
 def test_padded_transpose_is_equivalent(monkeypatch):
     """Rows of the cached transpose are padded to multiples of 4 with explicit zeros: same grad_B, bit for bit."""
     import torchsparsegradutils_b200 as tsgu
@@ -137,7 +172,7 @@ def test_padded_transpose_is_equivalent(monkeypatch):
     tsgu.clear_pattern_cache()
     A = W.uniform_rows_csr(2, 65536, 65536, 16, torch.float32, torch.int32, DEV, seed=7)
     B, G = W.dense_operands((2, 65536, 65536), 128, torch.float32, DEV, seed=8)
-    T = csr_pattern(A).transpose()
+    T = csr_pattern(A).transpose(optimise=True)  # (by default the layout is optimised on the second request)
     lens = T.rowptr[1:] - T.rowptr[:-1]
     assert bool((lens % 4 == 0).all()) and T.nnz_total > 2 * 65536 * 16 and int((T.perm < 0).sum()) == T.nnz_total - 2 * 65536 * 16
     _, _, gB_pad = _fwd_bwd(A, B, G)

@@ -8,12 +8,12 @@ index/layout helpers it depends on.  The arithmetic is hand-written sm_100a CUDA
 """
 from . import utils
 from .batch_mv import batch_sparse_mv
-from ._pattern import clear_pattern_cache, set_pattern_cache_capacity
+from ._pattern import clear_pattern_cache, prepare_pattern, set_pattern_cache_capacity
 from .graph import GraphedSparseMM
 from .rsample import rsample_transform
 from .encoders import PairwiseValueAssembler
 from .sddmm import block_diag_operand, lstsq_grad_A, sddmm, solve_grad_A
 from .sparse_matmul import SparseMatMul, sparse_mm
 
-__all__ = ["sparse_mm", "SparseMatMul", "sddmm", "solve_grad_A", "lstsq_grad_A", "block_diag_operand", "PairwiseValueAssembler", "batch_sparse_mv", "rsample_transform", "GraphedSparseMM", "utils", "clear_pattern_cache", "set_pattern_cache_capacity"]
+__all__ = ["sparse_mm", "SparseMatMul", "sddmm", "solve_grad_A", "lstsq_grad_A", "block_diag_operand", "PairwiseValueAssembler", "batch_sparse_mv", "rsample_transform", "GraphedSparseMM", "utils", "clear_pattern_cache", "prepare_pattern", "set_pattern_cache_capacity"]
 __version__ = "0.1.0"

@@ -33,6 +33,9 @@ _SIGNATURES = {
     "tsgu_error_string": (c_char_p, [_I]),
     "tsgu_launch_count": (_L, []),
     "tsgu_set_sm_margin": (_I, [_I]),
+    "tsgu_mailbox_create": (_I, [_Z, ctypes.POINTER(_P), ctypes.POINTER(_P)]),
+    "tsgu_mailbox_destroy": (_I, [_P]),
+    "tsgu_publish": (_I, [_P, _P, _Z, _P]),
     "tsgu_spmm_csr": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _I, _I, _P, _Z, _P]),
     "tsgu_spmm_csr_rowmap": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _I, _I, _P]),
     "tsgu_spmm_workspace_bytes": (_Z, [_L, _L, _L, _L, _I, _I]),
@@ -123,6 +126,37 @@ def stream_ptr(device: torch.device) -> int:
     if _raw_stream is not None and device.index is not None:
         return _raw_stream(device.index)
     return torch.cuda.current_stream(device).cuda_stream
+
+
+_MAILBOX_WORDS = 64  # int64 slots per host read
+_mailboxes = threading.local()
+
+
+def host_read(t: torch.Tensor) -> list:
+    """The values of a small integer CUDA tensor on the host: one publish kernel into this thread's mapped-memory
+    mailbox plus a stream synchronise (``tsgu_publish``) -- not ``.tolist()``, whose cudaMemcpy would wait behind any
+    bulk D2H traffic of the application."""
+    if not t.is_cuda:  # host-side unit tests of the pattern logic
+        return t.reshape(-1).long().tolist()
+    if t.dtype != torch.int64:
+        t = t.long()
+    t = t.contiguous().reshape(-1)
+    count = t.numel()
+    if count == 0:
+        return []
+    if count > _MAILBOX_WORDS:
+        raise ValueError(f"host_read carries at most {_MAILBOX_WORDS} values")
+    box = getattr(_mailboxes, "box", None)
+    if box is None:
+        host, dev = _P(), _P()
+        check(lib().tsgu_mailbox_create(_MAILBOX_WORDS * 8, ctypes.byref(host), ctypes.byref(dev)), "tsgu_mailbox_create")
+        view = (c_int64 * _MAILBOX_WORDS).from_address(host.value)
+        box = _mailboxes.box = (view, dev.value)  # lives as long as the thread (mapped memory is never recycled)
+    view, dev = box
+    with torch.cuda.device(t.device):
+        check(lib().tsgu_publish(t.data_ptr(), dev, count * 8, stream_ptr(t.device)), "tsgu_publish")
+        torch.cuda.current_stream(t.device).synchronize()
+    return list(view[:count])
 
 
 def ptr(t) -> int | None:

@@ -144,6 +144,7 @@ class CsrPattern:
     fingerprint: Optional[torch.Tensor] = field(default=None, repr=False)
     cache_key: Optional[tuple] = field(default=None, repr=False)
     _transpose: Optional["CsrPattern"] = field(default=None, repr=False)
+    _transpose_uses: int = field(default=0, repr=False)
     _uniform: Optional[bool] = field(default=None, repr=False)
     _lock: threading.Lock = field(default_factory=threading.Lock, repr=False)
 
@@ -162,17 +163,32 @@ class CsrPattern:
                 self._uniform = False
             else:
                 rp = self.rowptr.reshape(self.batch, -1) if self.rowptr_bstride == self.n + 1 else self.rowptr.reshape(1, -1)
-                longest = int((rp[:, 1:] - rp[:, :-1]).max())
+                longest = nat.host_read((rp[:, 1:] - rp[:, :-1]).max())[0]
                 self._uniform = longest <= 1.25 * (self.nnz_total / rows) + 1
         return self._uniform
 
-    def transpose(self) -> "CsrPattern":
-        """CSR of the transposes (flat over batch*m rows), built once by tsgu_csr_transpose."""
-        if self._transpose is None:
-            with self._lock:
-                if self._transpose is None:
-                    self._transpose = _build_transpose(self)
-        return self._transpose
+    def transpose(self, optimise: Optional[bool] = None) -> "CsrPattern":
+        """CSR of the transposes (flat over batch*m rows), built once by tsgu_csr_transpose.
+
+        The first request returns the plain transposed structure; the layout optimisations of the row-tile kernels
+        (rows sorted by length inside blocks, rows padded to whole gather groups: ~0.5 ms of index work that saves
+        ~0.02 ms per backward on a 1M-entry pattern) are applied from request number ``_LAYOUT_AFTER_USES`` (2) on, so
+        a pattern that is used once -- a new graph every step -- does not pay for them.  ``optimise=True`` applies
+        them now (GraphedSparseMM before capture, tests), ``False`` never upgrades on this call."""
+        t = self._transpose
+        if t is not None and "layout_pending" not in t.extras:
+            return t
+        with self._lock:
+            if self._transpose is None:
+                self._transpose = _build_transpose(self)
+            t = self._transpose
+            if "layout_pending" in t.extras:
+                if optimise is None:
+                    self._transpose_uses += 1
+                    optimise = self._transpose_uses >= _LAYOUT_AFTER_USES
+                if optimise and not torch.cuda.is_current_stream_capturing():
+                    t = self._transpose = _optimise_layout(t)
+        return t
 
 
 @dataclass
@@ -234,9 +250,49 @@ def choose_algo(rowptr: torch.Tensor, batch: int, n: int, nnz_total: int) -> int
     if forced is not None:
         return forced
     flat = rowptr.reshape(-1)  # batch == 1: torch batched CSR keeps a leading dim of 1
-    max_row = int((flat[1:] - flat[:-1]).max())
-    mean = nnz_total / n
-    return _SKEWED_ALGO if (max_row > 256 and max_row > 16 * mean) else nat.ALGO_AUTO
+    return _algo_from_max_row(nat.host_read((flat[1:] - flat[:-1]).max())[0], n, nnz_total)
+
+
+def _algo_from_max_row(max_row: int, n: int, nnz_total: int) -> int:
+    return _SKEWED_ALGO if (max_row > 256 and max_row > 16 * (nnz_total / n)) else nat.ALGO_AUTO
+
+
+def _needs_row_stats(batch: int, n: int, nnz_total: int) -> bool:
+    """Does choose_algo need the longest row (a device reduction + host read) for this pattern?"""
+    forced = _ALGO_ENV.get(os.environ.get("TSGU_B200_ALGO", "auto").lower())
+    return forced is None and batch == 1 and nnz_total > 0 and n > 0
+
+
+def _analyse(rowptr: torch.Tensor, colind: torch.Tensor, batch: int, n: int, m: int, rowptr_bstride: int, nnz_bstride: int,
+             nnz_total: int, idx: int, extra=None):
+    """Everything the host must know about a new pattern, gathered with ONE host read: the longest row (kernel family),
+    the verdict of a speculatively launched column-window plan, and optional extra device scalars of the caller.
+    Returns (algo, WindowPlan | None, extra values)."""
+    dev = rowptr.device
+    parts = []
+    want_rows = _needs_row_stats(batch, n, nnz_total)
+    if want_rows:
+        flat = rowptr.reshape(-1)
+        parts.append((flat[1:] - flat[:-1]).max().reshape(1).long())
+    launched = _window_plan_launch(rowptr, colind, batch, n, m, rowptr_bstride, nnz_bstride, nnz_total, idx)
+    if launched is not None:
+        parts.append(launched[2].long())
+    if extra is not None:
+        parts.append(extra.reshape(-1).long())
+    host = nat.host_read(torch.cat(parts)) if parts else []  # the one host sync
+    pos = 0
+    if want_rows:
+        algo = _algo_from_max_row(host[0], n, nnz_total)
+        pos = 1
+    else:
+        algo = choose_algo(rowptr, batch, n, nnz_total)  # forced / batched / empty: no device read
+    plan = None
+    if launched is not None:
+        failed, max_w, max_runs, max_entries = host[pos:pos + 4]
+        pos += 4
+        if failed == 0 and algo == nat.ALGO_AUTO:
+            plan = WindowPlan(launched[0], launched[1], launched[3], max_w, max_runs, max_entries)
+    return algo, plan, host[pos:]
 
 
 def _internal_idx(batch: int, rows: int, cols: int, nnz: int) -> int:
@@ -273,32 +329,43 @@ def window_limits():
     return _window_limits
 
 
+def _window_plan_launch(rowptr, colind, batch, n, m, rowptr_bstride, nnz_bstride, nnz_total, idx):
+    """Launch tsgu_window_plan if the pattern is large enough to be worth it; returns (lcol, desc, stats, tile_rows) with
+    the verdict still on the device, or None."""
+    rows = batch * n
+    if not (_WINDOW_ON and idx == nat.I32 and nnz_total >= _WINDOW_MIN_NNZ and rows >= _WINDOW_MIN_ROWS and m < _I32_MAX):
+        return None
+    lim = window_limits()
+    avg = nnz_total / rows
+    tile_rows = next((t for t in (32, 16, 8) if t <= lim["tile_rows"] and t * avg <= lim["entries"]), 0)
+    if not tile_rows:
+        return None
+    dev = rowptr.device
+    tiles = batch * (-(-n // tile_rows))
+    lcol = torch.empty(colind.numel(), dtype=torch.int16, device=dev)
+    desc = torch.empty((tiles, 32), dtype=torch.int32, device=dev)
+    stats = torch.empty(4, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().tsgu_window_plan(nat.ptr(rowptr), nat.ptr(colind), batch, n, rowptr_bstride, nnz_bstride, idx,
+                                             tile_rows, nat.ptr(lcol), nat.ptr(desc), nat.ptr(stats), nat.stream_ptr(dev)),
+                  "tsgu_window_plan")
+    return lcol, desc, stats, tile_rows
+
+
 def window_plan(p: "CsrPattern") -> Optional[WindowPlan]:
     """Column-window plan of a pattern, or None when the pattern is not structured enough (some tile of consecutive
-    rows touches more distinct columns / runs than a shared-memory window holds).  Built once per pattern by
-    tsgu_window_plan (one kernel, one host sync for the verdict) and cached with it."""
+    rows touches more distinct columns / runs than a shared-memory window holds).  Normally decided together with the
+    kernel family when the pattern is created (`_analyse`: one host read for both); built here on demand otherwise."""
     if "window" in p.extras:
         return p.extras["window"]
     plan = None
-    rows = p.batch * p.n
-    if (_WINDOW_ON and p.idx == nat.I32 and p.algo == nat.ALGO_AUTO and p.nnz_total >= _WINDOW_MIN_NNZ
-            and rows >= _WINDOW_MIN_ROWS and p.m < _I32_MAX):
-        lim = window_limits()
-        avg = p.nnz_total / rows
-        tile_rows = next((t for t in (32, 16, 8) if t <= lim["tile_rows"] and t * avg <= lim["entries"]), 0)
-        if tile_rows:
-            dev = p.device
-            tiles = p.batch * (-(-p.n // tile_rows))
-            lcol = torch.empty(p.colind.numel(), dtype=torch.int16, device=dev)
-            desc = torch.empty((tiles, 32), dtype=torch.int32, device=dev)
-            stats = torch.empty(4, dtype=torch.int32, device=dev)
-            with torch.cuda.device(dev):
-                nat.check(nat.lib().tsgu_window_plan(nat.ptr(p.rowptr), nat.ptr(p.colind), p.batch, p.n, p.rowptr_bstride,
-                                                     p.nnz_bstride, p.idx, tile_rows, nat.ptr(lcol), nat.ptr(desc),
-                                                     nat.ptr(stats), nat.stream_ptr(dev)), "tsgu_window_plan")
-            failed, max_w, max_runs, max_entries = stats.tolist()  # the one host sync of the plan
+    if p.algo == nat.ALGO_AUTO:
+        launched = _window_plan_launch(p.rowptr, p.colind, p.batch, p.n, p.m, p.rowptr_bstride, p.nnz_bstride, p.nnz_total,
+                                       p.idx)
+        if launched is not None:
+            failed, max_w, max_runs, max_entries = nat.host_read(launched[2])
             if failed == 0:
-                plan = WindowPlan(lcol, desc, tile_rows, max_w, max_runs, max_entries)
+                plan = WindowPlan(launched[0], launched[1], launched[3], max_w, max_runs, max_entries)
     p.extras["window"] = plan
     return plan
 
@@ -321,22 +388,41 @@ def _build_transpose(p: CsrPattern) -> CsrPattern:
     if p.perm is not None and p.nnz_total > 0:
         # entries of p are themselves a permutation of the caller's value storage: compose once
         permT = p.perm.to(odt).index_select(0, permT.long()) if p.perm.dtype != odt else p.perm.index_select(0, permT.long())
-    algo = choose_algo(rowptrT, p.batch, p.m, p.nnz_total)
     nnzT = p.nnz_total
+    lensT = (rowptrT[1:] - rowptrT[:-1]).long()
+    padded_total = ((lensT + (_ROW_PAD - 1)) // _ROW_PAD * _ROW_PAD).sum()  # device scalar, read with the other verdicts
+    algo, plan, (padded_total,) = _analyse(rowptrT, colindT, p.batch, p.m, p.n, p.m, 0, nnzT, out_idx, extra=padded_total)
     patT = CsrPattern(rowptrT, colindT, permT, p.batch, p.m, p.n, p.m, 0, nnzT, out_idx, algo=algo)
-    if algo == nat.ALGO_AUTO and nnzT >= _PAD_MIN_NNZ and window_plan(patT) is None:
-        # no column-window structure: the row-tile kernels take it.  Two layout optimisations of a structure WE own:
-        # rows sorted by length inside every item (the 4 rows a warp works on together then hold the same number of
-        # entries: Poisson-distributed lengths otherwise cost max-of-4 instead of the mean), and rows padded to whole
-        # gather groups (skipped if the padding would overflow a 32-bit rowptr)
-        row_map = None
-        if _SORT_ROWS:
-            rowptrT, colindT, permT, row_map = _sort_rows_by_length(rowptrT, colindT, permT, p.batch, p.m)
-        if out_idx == nat.I64 or nnzT + (_ROW_PAD - 1) * p.batch * p.m < _I32_MAX:
-            rowptrT, colindT, permT, nnzT = _pad_rows(rowptrT, colindT, permT, _ROW_PAD)
-        patT = CsrPattern(rowptrT, colindT, permT, p.batch, p.m, p.n, p.m, 0, nnzT, out_idx, algo=algo,
-                          row_map=row_map, padded=nnzT > p.nnz_total)
+    patT.extras["window"] = plan
+    if algo == nat.ALGO_AUTO and nnzT >= _PAD_MIN_NNZ and plan is None:
+        # no column-window structure: the row-tile kernels take it, and two layout optimisations of a structure WE own
+        # apply -- later, if the pattern turns out to be reused (CsrPattern.transpose).  No further host sync then: the
+        # padded size came with the verdicts above.
+        patT.extras["layout_pending"] = padded_total
     return _with_split(patT)
+
+
+_LAYOUT_AFTER_USES = int(os.environ.get("TSGU_B200_LAYOUT_AFTER_USES", "2"))
+
+
+def _optimise_layout(patT: CsrPattern) -> CsrPattern:
+    """Rows sorted by length inside blocks (the 4 rows a warp works on together then hold the same number of entries:
+    Poisson-distributed lengths otherwise cost max-of-4 instead of the mean), and rows padded to whole gather groups
+    (skipped if the padding would overflow a 32-bit rowptr).  Returns a new pattern; `patT` is left untouched for
+    whoever still holds it."""
+    padded_total = patT.extras["layout_pending"]
+    rowptrT, colindT, permT, row_map = patT.rowptr, patT.colind, patT.perm, None
+    cur = torch.cuda.current_stream(patT.device)
+    for t in (rowptrT, colindT, permT):
+        t.record_stream(cur)  # the caller drops patT right after; it may have been built under another stream
+    if _SORT_ROWS:
+        rowptrT, colindT, permT, row_map = _sort_rows_by_length(rowptrT, colindT, permT, patT.batch, patT.n)
+    if (patT.idx == nat.I64 or padded_total < _I32_MAX) and padded_total > patT.nnz_total:
+        rowptrT, colindT, permT = _pad_rows(rowptrT, colindT, permT, _ROW_PAD, padded_total)
+    new = CsrPattern(rowptrT, colindT, permT, patT.batch, patT.n, patT.m, patT.n, 0, permT.numel(), patT.idx,
+                     algo=patT.algo, row_map=row_map, padded=permT.numel() > patT.nnz_total)
+    new.extras["window"] = None
+    return new
 
 
 def _split_bound() -> int:
@@ -388,30 +474,30 @@ _ROW_PAD = 4          # the row-split kernels consume a row in groups of >= 4 en
 _PAD_MIN_NNZ = 1 << 18
 
 
-def _pad_rows(rowptr: torch.Tensor, colind: torch.Tensor, perm: torch.Tensor, mult: int):
-    """Pad every row of a structure WE own (a transpose) to a multiple of `mult` entries.
+def _pad_rows(rowptr: torch.Tensor, colind: torch.Tensor, perm: torch.Tensor, mult: int, total: int):
+    """Pad every row of a structure WE own (a transpose) to a multiple of `mult` entries; `total` is the padded entry
+    count (known to the caller: no host sync here).
 
     Rows of a transposed matrix have Poisson-like lengths, so most rows end in a partly filled group of
     gathers; that ragged path costs the transposed SpMM 20-60 % (profiles/r1_gather_ceilings.txt).
     Padding entries repeat the row's last column (an L1-hot dense row) and carry perm = -1, which the
     value gather turns into an explicit 0, so the product is unchanged.  One-off, cached with the pattern.
     """
+    dev = rowptr.device
     lens = (rowptr[1:] - rowptr[:-1]).long()
     plen = (lens + (mult - 1)) // mult * mult
-    if bool((plen == lens).all()):
-        return rowptr, colind, perm, colind.numel()
     rows = lens.numel()
-    new_rowptr = torch.zeros(rows + 1, dtype=torch.int64, device=rowptr.device)
+    nnz = colind.numel()
+    new_rowptr = torch.zeros(rows + 1, dtype=torch.int64, device=dev)
     new_rowptr[1:] = plen.cumsum(0)
-    total = int(new_rowptr[-1])
-    row_of = torch.repeat_interleave(torch.arange(rows, device=rowptr.device), lens)
-    new_pos = new_rowptr[row_of] + (torch.arange(colind.numel(), device=rowptr.device) - rowptr.long()[row_of])
+    row_of = torch.repeat_interleave(torch.arange(rows, device=dev), lens, output_size=nnz)
+    new_pos = new_rowptr[row_of] + (torch.arange(nnz, device=dev) - rowptr.long()[row_of])
     last_col = colind[(rowptr[1:].long() - 1).clamp_(min=0)]  # unused for empty rows (plen == 0)
-    colind_p = torch.repeat_interleave(last_col, plen)
+    colind_p = torch.repeat_interleave(last_col, plen, output_size=total)
     colind_p[new_pos] = colind
-    perm_p = torch.full((total,), -1, dtype=perm.dtype, device=perm.device)
+    perm_p = torch.full((total,), -1, dtype=perm.dtype, device=dev)
     perm_p[new_pos] = perm
-    return new_rowptr.to(rowptr.dtype), colind_p, perm_p, total
+    return new_rowptr.to(rowptr.dtype), colind_p, perm_p
 
 
 def _cache_get(key, index_tensors=()):
@@ -456,9 +542,11 @@ def csr_pattern(A: torch.Tensor) -> CsrPattern:
     # dispatcher fall to the non-staged kernels (measured on a row block of config 4: 15.7 ms instead of 0.93 ms)
     crow_c, col_c = aligned_contiguous(crow), aligned_contiguous(col)
     nnz_item = col_c.shape[-1]
-    pat = _with_split(CsrPattern(crow_c, col_c, None, batch, n, m, n + 1, nnz_item, batch * nnz_item,
-                                 nat.idx_enum(crow.dtype), algo=choose_algo(crow_c, batch, n, batch * nnz_item),
+    idx = nat.idx_enum(crow.dtype)
+    algo, plan, _ = _analyse(crow_c, col_c, batch, n, m, n + 1, nnz_item, batch * nnz_item, idx)
+    pat = _with_split(CsrPattern(crow_c, col_c, None, batch, n, m, n + 1, nnz_item, batch * nnz_item, idx, algo=algo,
                                  keep=(crow, col)))
+    pat.extras["window"] = plan
     pat.cache_key = key
     _cache_put(key, pat, (crow, col))
     return pat
@@ -510,8 +598,10 @@ def _coo_to_flat_csr(indices: torch.Tensor, batch: int, n: int, m: int, perm: Op
         nat.check(nat.lib().tsgu_coo_to_csr(nat.ptr(indices), ndim, nnz, indices.stride(0), batch, n, nat.ptr(perm),
                                             nat.ptr(rowptr), nat.ptr(colind), idx, nat.stream_ptr(dev)),
                   "tsgu_coo_to_csr")
-    return _with_split(CsrPattern(rowptr, colind, perm, batch, n, m, n, 0, nnz, idx, algo=choose_algo(rowptr, batch, n, nnz),
-                                  keep=keep))
+    algo, plan, _ = _analyse(rowptr, colind, batch, n, m, n, 0, nnz, idx)
+    pat = _with_split(CsrPattern(rowptr, colind, perm, batch, n, m, n, 0, nnz, idx, algo=algo, keep=keep))
+    pat.extras["window"] = plan
+    return pat
 
 
 def coo_pattern(A: torch.Tensor) -> CooPattern:
@@ -549,7 +639,7 @@ def coo_pattern(A: torch.Tensor) -> CooPattern:
             if nnz > 1:
                 first = torch.ones(nnz, dtype=torch.bool, device=ind.device)
                 first[1:] = (srt[:, 1:] != srt[:, :-1]).any(dim=0)
-                dup = not bool(first.all())  # one-off host sync per pattern (sizes the gradient)
+                dup = not nat.host_read(first.all())[0]  # one-off host sync per pattern (sizes the gradient)
             if not dup:
                 csr = _coo_to_flat_csr(ind, batch, n, m, perm, idx, keep=(ind,))
                 pat = CooPattern(csr, None, srt, None, perm, nnz)
@@ -564,3 +654,24 @@ def coo_pattern(A: torch.Tensor) -> CooPattern:
     pat.cache_key = key
     _cache_put(key, pat, (ind_key,))
     return pat
+
+
+def prepare_pattern(A: torch.Tensor, backward: bool = True, reuse: bool = True) -> None:
+    """Build (and cache) everything that depends only on A's sparsity pattern -- COO order / flat CSR, the kernel-family
+    choice, column-window plans and, with `backward`, the transpose -- ahead of the first ``sparse_mm(A, .)``.
+
+    The builds need only A's index tensors, so a data loader can issue them as soon as those have arrived on the device,
+    while the dense operands are still in flight (bench.py's end-to-end leg does exactly that); ``sparse_mm`` then finds
+    the pattern in the cache.  Purely an optimisation: ``sparse_mm`` builds whatever is missing on first use.
+
+    `reuse` says the pattern will serve many steps, so the transposed structure gets its layout optimisations right
+    away (``CsrPattern.transpose``); pass False for a pattern that lives for a single step."""
+    if A.layout == torch.sparse_csr:
+        csr = csr_pattern(A)
+    elif A.layout == torch.sparse_coo:
+        csr = coo_pattern(A).csr
+    else:
+        raise ValueError("A should be in either COO or CSR sparse format")
+    window_plan(csr)
+    if backward:
+        csr.transpose(optimise=True if reuse else False)

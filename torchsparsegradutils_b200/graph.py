@@ -54,6 +54,7 @@ class GraphedSparseMM:
             # LRU pattern cache happens to hold (it may have capacity 0, or evict the entry between steps).
             self._pattern = csr_pattern(self._A) if self._csr else coo_pattern(self._A)
             pin_pattern(self._pattern.cache_key, self._pattern)
+            (self._pattern if self._csr else self._pattern.csr).transpose(optimise=True)  # final layout before capture
             for _ in range(max(warmup, 1)):
                 step()
         torch.cuda.current_stream(dev).wait_stream(side)

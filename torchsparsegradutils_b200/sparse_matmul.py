@@ -149,9 +149,13 @@ def _backward_two_streams(ctx, grad):
     side = _side_streams.get(dev.index)
     if side is None:
         side = _side_streams[dev.index] = torch.cuda.Stream(dev)
+    pat = ctx.pattern
+    # a transposed structure that must still be built (or get its layout upgrade) is built HERE: tensors a cached
+    # pattern owns are allocated -- and the ones it replaces freed -- under the caller's stream, never the side stream
+    patT = (pat if isinstance(pat, CsrPattern) else pat.csr).transpose()
     side.wait_stream(main)  # fork (under graph capture: a parallel branch of the graph)
     with torch.cuda.stream(side):
-        gradB = _grad_B(ctx, grad)
+        gradB = _grad_B(ctx, grad, patT)
     gradA = _grad_A(ctx, grad)
     main.wait_stream(side)  # join
     gradB.record_stream(main)
@@ -176,7 +180,7 @@ def _grad_A(ctx, grad):
     return torch.sparse_coo_tensor(pat.grad_indices, v, A.shape)
 
 
-def _grad_B(ctx, grad):
+def _grad_B(ctx, grad, patT=None):
     """grad_B = A^T grad through the cached transposed structure (reference sparse_matmul.py:222-232)."""
     saved = ctx.saved_tensors
     A = saved[0]
@@ -192,7 +196,7 @@ def _grad_B(ctx, grad):
     want = None
     if ctx.B_strides is not None:  # ask for B's own layout; kernels that can write it directly save the re-stride pass
         want = tuple(ctx.B_strides) if ctx.batched else (ctx.B_shape[0] * ctx.B_shape[1],) + tuple(ctx.B_strides)
-    gradB = _ops.spmm(csr.transpose(), vals, grad, tag="spmm_gradB", out_strides=want)
+    gradB = _ops.spmm(csr.transpose() if patT is None else patT, vals, grad, tag="spmm_gradB", out_strides=want)
     gradB = gradB if ctx.batched else gradB[0]
     if ctx.B_strides is not None and tuple(gradB.stride()) != tuple(ctx.B_strides):
         gradB = _ops.restride_like(gradB, ctx.B_shape, ctx.B_strides)
