@@ -164,7 +164,7 @@ class CsrPattern:
             else:
                 rp = self.rowptr.reshape(self.batch, -1) if self.rowptr_bstride == self.n + 1 else self.rowptr.reshape(1, -1)
                 longest = nat.host_read((rp[:, 1:] - rp[:, :-1]).max())[0]
-                self._uniform = longest <= 1.25 * (self.nnz_total / rows) + 1
+                self._uniform = _uniform_from(longest, rows, self.nnz_total)
         return self._uniform
 
     def transpose(self, optimise: Optional[bool] = None) -> "CsrPattern":
@@ -267,23 +267,28 @@ def _analyse(rowptr: torch.Tensor, colind: torch.Tensor, batch: int, n: int, m: 
              nnz_total: int, idx: int, extra=None):
     """Everything the host must know about a new pattern, gathered with ONE host read: the longest row (kernel family),
     the verdict of a speculatively launched column-window plan, and optional extra device scalars of the caller.
-    Returns (algo, WindowPlan | None, extra values)."""
-    dev = rowptr.device
+    Returns (algo, WindowPlan | None, extra values, longest row | None)."""
     parts = []
     want_rows = _needs_row_stats(batch, n, nnz_total)
-    if want_rows:
-        flat = rowptr.reshape(-1)
-        parts.append((flat[1:] - flat[:-1]).max().reshape(1).long())
     launched = _window_plan_launch(rowptr, colind, batch, n, m, rowptr_bstride, nnz_bstride, nnz_total, idx)
+    # the longest row rides along whenever something is read anyway (it also answers CsrPattern.uniform_rows, which would
+    # otherwise cost the first forward a host sync of its own)
+    with_rows = nnz_total > 0 and n > 0 and (want_rows or launched is not None or extra is not None)
+    if with_rows:
+        flat = rowptr.reshape(-1)  # differences across item boundaries of a (b, n+1) rowptr are <= 0: harmless for a max
+        parts.append((flat[1:] - flat[:-1]).max().reshape(1).long())
     if launched is not None:
         parts.append(launched[2].long())
     if extra is not None:
         parts.append(extra.reshape(-1).long())
     host = nat.host_read(torch.cat(parts)) if parts else []  # the one host sync
     pos = 0
-    if want_rows:
-        algo = _algo_from_max_row(host[0], n, nnz_total)
+    max_row = None
+    if with_rows:
+        max_row = host[0]
         pos = 1
+    if want_rows:
+        algo = _algo_from_max_row(max_row, n, nnz_total)
     else:
         algo = choose_algo(rowptr, batch, n, nnz_total)  # forced / batched / empty: no device read
     plan = None
@@ -292,7 +297,14 @@ def _analyse(rowptr: torch.Tensor, colind: torch.Tensor, batch: int, n: int, m: 
         pos += 4
         if failed == 0 and algo == nat.ALGO_AUTO:
             plan = WindowPlan(launched[0], launched[1], launched[3], max_w, max_runs, max_entries)
-    return algo, plan, host[pos:]
+    return algo, plan, host[pos:], max_row
+
+
+def _uniform_from(max_row: Optional[int], rows: int, nnz_total: int) -> Optional[bool]:
+    """CsrPattern.uniform_rows from an already known longest row (None: not known, read lazily)."""
+    if rows == 0 or nnz_total == 0:
+        return False
+    return None if max_row is None else max_row <= 1.25 * (nnz_total / rows) + 1
 
 
 def _internal_idx(batch: int, rows: int, cols: int, nnz: int) -> int:
@@ -391,8 +403,10 @@ def _build_transpose(p: CsrPattern) -> CsrPattern:
     nnzT = p.nnz_total
     lensT = (rowptrT[1:] - rowptrT[:-1]).long()
     padded_total = ((lensT + (_ROW_PAD - 1)) // _ROW_PAD * _ROW_PAD).sum()  # device scalar, read with the other verdicts
-    algo, plan, (padded_total,) = _analyse(rowptrT, colindT, p.batch, p.m, p.n, p.m, 0, nnzT, out_idx, extra=padded_total)
+    algo, plan, (padded_total,), max_row = _analyse(rowptrT, colindT, p.batch, p.m, p.n, p.m, 0, nnzT, out_idx,
+                                                    extra=padded_total)
     patT = CsrPattern(rowptrT, colindT, permT, p.batch, p.m, p.n, p.m, 0, nnzT, out_idx, algo=algo)
+    patT._uniform = _uniform_from(max_row, p.batch * p.m, nnzT)
     patT.extras["window"] = plan
     if algo == nat.ALGO_AUTO and nnzT >= _PAD_MIN_NNZ and plan is None:
         # no column-window structure: the row-tile kernels take it, and two layout optimisations of a structure WE own
@@ -422,6 +436,7 @@ def _optimise_layout(patT: CsrPattern) -> CsrPattern:
     new = CsrPattern(rowptrT, colindT, permT, patT.batch, patT.n, patT.m, patT.n, 0, permT.numel(), patT.idx,
                      algo=patT.algo, row_map=row_map, padded=permT.numel() > patT.nnz_total)
     new.extras["window"] = None
+    new._uniform = patT._uniform
     return new
 
 
@@ -543,9 +558,10 @@ def csr_pattern(A: torch.Tensor) -> CsrPattern:
     crow_c, col_c = aligned_contiguous(crow), aligned_contiguous(col)
     nnz_item = col_c.shape[-1]
     idx = nat.idx_enum(crow.dtype)
-    algo, plan, _ = _analyse(crow_c, col_c, batch, n, m, n + 1, nnz_item, batch * nnz_item, idx)
+    algo, plan, _, max_row = _analyse(crow_c, col_c, batch, n, m, n + 1, nnz_item, batch * nnz_item, idx)
     pat = _with_split(CsrPattern(crow_c, col_c, None, batch, n, m, n + 1, nnz_item, batch * nnz_item, idx, algo=algo,
                                  keep=(crow, col)))
+    pat._uniform = _uniform_from(max_row, batch * n, batch * nnz_item)
     pat.extras["window"] = plan
     pat.cache_key = key
     _cache_put(key, pat, (crow, col))
@@ -598,8 +614,9 @@ def _coo_to_flat_csr(indices: torch.Tensor, batch: int, n: int, m: int, perm: Op
         nat.check(nat.lib().tsgu_coo_to_csr(nat.ptr(indices), ndim, nnz, indices.stride(0), batch, n, nat.ptr(perm),
                                             nat.ptr(rowptr), nat.ptr(colind), idx, nat.stream_ptr(dev)),
                   "tsgu_coo_to_csr")
-    algo, plan, _ = _analyse(rowptr, colind, batch, n, m, n, 0, nnz, idx)
+    algo, plan, _, max_row = _analyse(rowptr, colind, batch, n, m, n, 0, nnz, idx)
     pat = _with_split(CsrPattern(rowptr, colind, perm, batch, n, m, n, 0, nnz, idx, algo=algo, keep=keep))
+    pat._uniform = _uniform_from(max_row, batch * n, nnz)
     pat.extras["window"] = plan
     return pat
 
