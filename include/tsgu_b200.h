@@ -218,6 +218,11 @@ TSGU_API int tsgu_gather_values(const void* in, const void* perm, void* out, int
 TSGU_API int tsgu_scatter_values(const void* in, const void* perm, void* out, int64_t count, int64_t out_count,
                         int val_dtype, int idx_dtype, void* stream);
 
+/* *out (uint64, zeroed by the caller) += position-weighted checksum of an index array of `count` elements.  The host
+ * side keeps one per cached sparsity pattern and re-checks it on a thinning schedule of cache hits, so index buffers that
+ * were rewritten in place under a cached pattern raise instead of silently reusing the old structure. */
+TSGU_API int tsgu_fingerprint(const void* data, int64_t count, int idx_dtype, void* out, void* stream);
+
 /* Batched CSR (crow (b, n+1), col (b, nnz)) -> block-diagonal CSR over b*n rows / b*m columns in one pass: the index
  * arithmetic of sparse_block_diag (utils/utils.py:604-645) as the solves need it (sparse_solve.py:172-174). */
 TSGU_API int tsgu_block_diag_csr(const void* crow, const void* col, int64_t batch, int64_t n, int64_t m, int64_t nnz,

@@ -10,7 +10,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
-from torchsparsegradutils_b200 import sparse_mm  # noqa: E402
+from torchsparsegradutils_b200 import _pattern, sparse_mm  # noqa: E402
 
 cfg_name = sys.argv[1] if len(sys.argv) > 1 else "2"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
@@ -30,5 +30,6 @@ for name, env in combos:
     for k in ("TSGU_E2E_SLOTS", "TSGU_E2E_WHATIF_NO_D2H", "TSGU_E2E_WHATIF_WARM"):
         os.environ.pop(k, None)
     os.environ.update(env)
+    _pattern._VERIFY = "0" if "TSGU_E2E_WHATIF_WARM" in env else os.environ.get("TSGU_B200_VERIFY_PATTERN", "sampled")  # the warm what-if reuses stale patterns on purpose
     r = bench.run_e2e(A.detach(), B.detach(), G, steps, dev, None, sparse_mm)
     print(f"[{name}] ms/step {r['ms_per_step']:.3f} verified {r['results_verified']}", file=sys.stderr, flush=True)

@@ -681,22 +681,49 @@ def test_pattern_cache_byte_cap_evicts():
         tsgu.clear_pattern_cache()
 
 
-def test_verify_mode_detects_rewritten_index_memory(monkeypatch):
-    """TSGU_B200_VERIFY_PATTERN=1 (debug mode): an in-place rewrite of index memory through an alias is caught."""
+@pytest.mark.parametrize("mode", ["sampled", "1", "0"])
+def test_rewritten_index_memory_under_a_cached_pattern_is_detected(mode, monkeypatch):
+    """An in-place rewrite of index memory through an alias is invisible to the cache key; the stored checksum catches
+    it on the first reuse (default: re-checked on hits 1, 2, 4, ...; "1": every hit; "0": checks off, stale reuse)."""
     import torchsparsegradutils_b200 as tsgu
     from torchsparsegradutils_b200 import _pattern, sparse_mm
 
     tsgu.clear_pattern_cache()
-    monkeypatch.setattr(_pattern, "_VERIFY", True)
+    monkeypatch.setattr(_pattern, "_VERIFY", mode)
     idx = torch.tensor([[0, 1], [0, 1]], device=DEV)
     A = torch.sparse_coo_tensor(idx, torch.ones(2, device=DEV), (2, 2))
     B = torch.tensor([[1.0, 2.0], [3.0, 4.0]], device=DEV)
     assert torch.equal(sparse_mm(A, B), B)
     idx[1] = torch.tensor([1, 0], device=DEV)  # alias write: no version bump on A._indices()
-    with pytest.raises(RuntimeError, match="rewritten in place"):
-        sparse_mm(A, B)
+    if mode == "0":
+        assert torch.equal(sparse_mm(A, B), B)  # the frozen-pattern contract, unchecked: the OLD pattern is used
+    elif mode == "1":
+        with pytest.raises(RuntimeError, match="rewritten in place"):
+            sparse_mm(A, B)
+    else:  # checked on the first reuse, reported by the next hit after the check has landed
+        with pytest.raises(RuntimeError, match="rewritten in place.*deferred"):
+            for _ in range(3):
+                sparse_mm(A, B)
+                torch.cuda.synchronize()
     tsgu.clear_pattern_cache()
     assert torch.equal(sparse_mm(A, B), B.flip(0))
+    # CSR, int32, large enough for the multi-block checksum kernel; a long run of clean hits stays clean
+    crow = torch.arange(0, 4 * 3000 + 1, 4, device=DEV, dtype=torch.int32)
+    col = (torch.arange(4 * 3000, device=DEV, dtype=torch.int32) * 7) % 3000
+    Ac = torch.sparse_csr_tensor(crow, col, torch.ones(4 * 3000, device=DEV), (3000, 3000))
+    Bc = torch.randn(3000, 8, device=DEV)
+    ref = sparse_mm(Ac, Bc)
+    for _ in range(9):
+        assert torch.equal(sparse_mm(Ac, Bc), ref)
+    col[5] = (col[5] + 1) % 3000
+    if mode == "1":
+        with pytest.raises(RuntimeError, match="rewritten in place"):
+            sparse_mm(Ac, Bc)
+    elif mode == "sampled":  # hits 10..15 are not checked, hit 16 is -- deferred: a later hit reports it
+        with pytest.raises(RuntimeError, match="rewritten in place.*deferred"):
+            for _ in range(12):
+                sparse_mm(Ac, Bc)
+                torch.cuda.synchronize()
     tsgu.clear_pattern_cache()
 
 

@@ -36,6 +36,7 @@ _SIGNATURES = {
     "tsgu_mailbox_create": (_I, [_Z, ctypes.POINTER(_P), ctypes.POINTER(_P)]),
     "tsgu_mailbox_destroy": (_I, [_P]),
     "tsgu_publish": (_I, [_P, _P, _Z, _P]),
+    "tsgu_fingerprint": (_I, [_P, _L, _I, _P, _P]),
     "tsgu_spmm_csr": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _I, _I, _P, _Z, _P]),
     "tsgu_spmm_csr_rowmap": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _L, _I, _I, _I, _P]),
     "tsgu_spmm_workspace_bytes": (_Z, [_L, _L, _L, _L, _I, _I]),

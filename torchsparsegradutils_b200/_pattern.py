@@ -13,9 +13,10 @@ keeps a reference to those tensors, so their storage cannot be recycled for a di
 entry lives.  What the key cannot see is an in-place write through an *unrelated alias* of the same storage
 (``idx.copy_(new)`` on the buffer a sparse tensor was built from: torch gives ``_indices()`` /
 ``crow_indices()`` their own version counters): while a pattern is cached its index memory is **frozen**;
-call ``clear_pattern_cache()`` after rewriting index buffers in place, or run with
-``TSGU_B200_VERIFY_PATTERN=1``, which re-checksums the index arrays on every hit (one host sync per call; a
-debug mode).  Entries are evicted LRU under both an entry cap and a byte cap (``set_pattern_cache_capacity``,
+call ``clear_pattern_cache()`` after rewriting index buffers in place.  A violation does not go unnoticed: every
+entry stores a checksum of its index arrays (``tsgu_fingerprint``) which is re-checked on cache hits number 1, 2, 4,
+8, ... and a mismatch raises -- by a deferred comparison on a following hit, so that no call synchronises with the
+device because of it.  ``TSGU_B200_VERIFY_PATTERN=1`` checks every hit on the spot (a host read per call), ``=0`` never.  Entries are evicted LRU under both an entry cap and a byte cap (``set_pattern_cache_capacity``,
 ``TSGU_B200_PATTERN_CACHE_BYTES``); ``clear_pattern_cache()`` drops everything.  Objects that must not lose
 their pattern to eviction (``GraphedSparseMM``) pin it with :func:`pin_pattern`.
 """
@@ -35,7 +36,7 @@ from . import _native as nat
 
 _CACHE_CAPACITY = 16
 _CACHE_BYTES = int(os.environ.get("TSGU_B200_PATTERN_CACHE_BYTES", str(8 << 30)))  # derived structures + kept index tensors
-_VERIFY = os.environ.get("TSGU_B200_VERIFY_PATTERN", "0") == "1"
+_VERIFY = os.environ.get("TSGU_B200_VERIFY_PATTERN", "sampled")  # "1": every hit, "0": never, else hits 1, 2, 4, 8, ...
 _cache: "OrderedDict[tuple, object]" = OrderedDict()
 _pinned: "weakref.WeakValueDictionary[tuple, object]" = weakref.WeakValueDictionary()
 _cache_lock = threading.Lock()
@@ -104,14 +105,29 @@ def _evict_locked() -> None:
 
 
 def _fingerprint(*tensors: torch.Tensor) -> torch.Tensor:
-    """Position-weighted checksum of index arrays (device scalar); TSGU_B200_VERIFY_PATTERN only."""
-    acc = None
-    for t in tensors:
-        f = t.reshape(-1).to(torch.int64)
-        w = (torch.arange(f.numel(), device=f.device, dtype=torch.int64) % 65521) + 1
-        c = (f * w).sum() + f.numel()
-        acc = c if acc is None else acc * 1000003 + c
-    return acc
+    """Position-weighted checksums of index arrays, one int64 per array, on the device (``tsgu_fingerprint``: one small
+    kernel per array, no host sync)."""
+    dev = tensors[0].device
+    if not tensors[0].is_cuda:  # host-side unit tests
+        return torch.stack([(t.reshape(-1).long() * (torch.arange(t.numel()) % 65521 + 1)).sum() for t in tensors])
+    out = torch.zeros(len(tensors), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        for k, t in enumerate(tensors):
+            if t.dim() > 1 and t.stride(0) == 0:
+                t = t[0]  # an expanded batch view (PairwiseValueAssembler): every item is the same memory
+            t = t if t.is_contiguous() else t.contiguous()
+            nat.check(nat.lib().tsgu_fingerprint(t.data_ptr(), t.numel(), nat.idx_enum(t.dtype), out[k:].data_ptr(),
+                                                 nat.stream_ptr(dev)), "tsgu_fingerprint")
+    return out
+
+
+def _verify_due(hits: int) -> bool:
+    """Which cache hits re-check the fingerprint: all of them ("1"), none ("0"), or -- the default -- hits number
+    1, 2, 4, 8, ...: the usual mistake (a static index buffer refilled for the next step) is caught on the first
+    reuse, and a long training run pays a logarithmic number of checks (each: two small kernels and one host read)."""
+    if _VERIFY == "1":
+        return True
+    return _VERIFY != "0" and (hits & (hits - 1)) == 0
 
 
 def pin_pattern(key, pattern) -> None:
@@ -522,17 +538,44 @@ def _cache_get(key, index_tensors=()):
             _cache.move_to_end(key)
         else:
             hit = _pinned.get(key)
-    if hit is not None and _VERIFY:
-        fp = getattr(hit, "fingerprint", None)
-        if fp is not None and not bool(fp == _fingerprint(*index_tensors)):
-            raise RuntimeError(
-                "torchsparsegradutils_b200: the index memory of a cached sparsity pattern was rewritten in place "
-                "(pattern memory is frozen while cached); call clear_pattern_cache() after editing index buffers")
+    if hit is not None and index_tensors and getattr(hit, "fingerprint", None) is not None:
+        _check_fingerprint(hit, index_tensors)
     return hit
 
 
+_REWRITTEN = ("torchsparsegradutils_b200: the index memory of a cached sparsity pattern was rewritten in place "
+              "(pattern memory is frozen while cached); call clear_pattern_cache() after editing index buffers")
+
+
+def _check_fingerprint(hit, index_tensors) -> None:
+    """Re-check the checksum of a cached pattern's index arrays on the hits _verify_due() selects.  In the default mode
+    the check is asynchronous -- two small kernels plus a 32-byte copy now, the comparison on a later hit -- so no call
+    ever synchronises with the device because of it (a host read on the first reuse stalled a loader pipeline that
+    prepares patterns ahead: bench.py's end-to-end leg, +1.5 ms per step); TSGU_B200_VERIFY_PATTERN=1 checks on the spot."""
+    hits = hit.hits = getattr(hit, "hits", 0) + 1
+    pending = getattr(hit, "pending_check", None)
+    if pending is not None and pending[0].query():
+        hit.pending_check = None
+        got = pending[1].tolist()
+        if got[:len(got) // 2] != got[len(got) // 2:]:
+            raise RuntimeError(_REWRITTEN + " (detected by a deferred check: results since the rewrite used the old pattern)")
+    if not _verify_due(hits) or (index_tensors[0].is_cuda and torch.cuda.is_current_stream_capturing()):
+        return
+    pair = torch.cat([hit.fingerprint, _fingerprint(*index_tensors)])
+    if _VERIFY == "1" or not pair.is_cuda:
+        got = nat.host_read(pair)
+        if got[:len(got) // 2] != got[len(got) // 2:]:
+            raise RuntimeError(_REWRITTEN)
+    elif getattr(hit, "pending_check", None) is None:
+        landed = torch.empty(pair.numel(), dtype=torch.int64, pin_memory=True)
+        landed.copy_(pair, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(pair.device))
+        hit.pending_check = (done, landed)
+
+
 def _cache_put(key, value, index_tensors=()):
-    if _VERIFY:
+    if _VERIFY != "0" and index_tensors:
         value.fingerprint = _fingerprint(*index_tensors)
     if _CACHE_CAPACITY == 0:
         return

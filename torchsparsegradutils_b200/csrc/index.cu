@@ -288,6 +288,19 @@ __global__ void __launch_bounds__(256) scatter_values_kernel(const V* __restrict
   }
 }
 
+// Position-weighted checksum of an index array, accumulated into *out (integer atomics: order independent, so the
+// value is deterministic).  The pattern cache uses it to notice index memory that was rewritten in place.
+template <typename I>
+__global__ void __launch_bounds__(256) fingerprint_kernel(const I* __restrict__ x, int64_t count,
+                                                          unsigned long long* __restrict__ out) {
+  unsigned long long acc = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    acc += (unsigned long long)(long long)__ldg(x + i) * (unsigned long long)(i % 65521 + 1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc != 0) atomicAdd(out, acc);
+}
+
 // Batched CSR (b, n+1) / (b, nnz) -> the block-diagonal CSR over b*n rows and b*m columns that the reference assembles
 // item by item (utils/utils.py:604-645): crow_out[t*n + r] = crow[t, r] + t*nnz, col_out[t*nnz + e] = col[t, e] + t*m.
 template <typename I>
@@ -605,6 +618,18 @@ extern "C" int tsgu_block_diag_csr(const void* crow, const void* col, int64_t ba
   TSGU_DISPATCH_IDX(idx_dtype, {
     block_diag_csr_kernel<I><<<blocks_for(batch * n + 1 + batch * nnz, 256), 256, 0, s>>>(
         (const I*)crow, (const I*)col, batch, n, m, nnz, (I*)crow_out, (I*)col_out);
+    count_launch();
+  });
+  return launch_status();
+}
+
+extern "C" int tsgu_fingerprint(const void* data, int64_t count, int idx_dtype, void* out, void* stream) {
+  if (count < 0 || !out) return TSGU_ERR_SHAPE;
+  if (count == 0) return 0;
+  cudaStream_t s = as_stream(stream);
+  const unsigned blocks = min(blocks_for(count, 256 * 8), 148u * 8u);
+  TSGU_DISPATCH_IDX(idx_dtype, {
+    fingerprint_kernel<I><<<blocks, 256, 0, s>>>((const I*)data, count, (unsigned long long*)out);
     count_launch();
   });
   return launch_status();
