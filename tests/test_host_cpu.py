@@ -188,6 +188,27 @@ def test_uniform_rows_gate_of_k_slicing():
     assert not pat(torch.zeros(7, dtype=torch.int32), 1, 6, 6, 0).uniform_rows
 
 
+def test_pattern_checksum_schedule_and_host_fingerprint(monkeypatch):
+    """Which cache hits re-check a pattern's index checksum (default 1, 2, 4, 8, ...; "1" all; "0" none), the host
+    restatement of tsgu_fingerprint (position-weighted sum: order of equal values matters), and the longest-row rule
+    that `_analyse` fills `uniform_rows` from."""
+    import torch
+
+    from torchsparsegradutils_b200 import _pattern
+
+    monkeypatch.setattr(_pattern, "_VERIFY", "sampled")
+    assert [h for h in range(1, 40) if _pattern._verify_due(h)] == [1, 2, 4, 8, 16, 32]
+    monkeypatch.setattr(_pattern, "_VERIFY", "1")
+    assert all(_pattern._verify_due(h) for h in range(1, 10))
+    monkeypatch.setattr(_pattern, "_VERIFY", "0")
+    assert not any(_pattern._verify_due(h) for h in range(1, 10))
+    a = torch.tensor([3, 1, 2], dtype=torch.int32)
+    fa, fb = _pattern._fingerprint(a, a.long()), _pattern._fingerprint(a.flip(0), a.long())
+    assert fa.tolist() == [3 * 1 + 1 * 2 + 2 * 3] * 2 and fb[0] != fa[0] and fb[1] == fa[1]
+    assert _pattern._uniform_from(None, 4, 16) is None and _pattern._uniform_from(5, 0, 0) is False
+    assert _pattern._uniform_from(6, 4, 16) is True and _pattern._uniform_from(7, 4, 16) is False  # 1.25 * 4 + 1 = 6
+
+
 def test_bench_stdout_carries_only_the_json_line(tmp_path):
     """bench.py's contract: ONE JSON line on stdout.  Anything else written to fd 1 while it runs (NCCL prints its
     version banner there under torchrun) must end up on stderr."""

@@ -712,6 +712,7 @@ def test_rewritten_index_memory_under_a_cached_pattern_is_detected(mode, monkeyp
     col = (torch.arange(4 * 3000, device=DEV, dtype=torch.int32) * 7) % 3000
     Ac = torch.sparse_csr_tensor(crow, col, torch.ones(4 * 3000, device=DEV), (3000, 3000))
     Bc = torch.randn(3000, 8, device=DEV)
+    assert _pattern._fingerprint(crow, col).tolist() == _pattern._fingerprint(crow.cpu(), col.cpu()).tolist()  # kernel == host restatement
     ref = sparse_mm(Ac, Bc)
     for _ in range(9):
         assert torch.equal(sparse_mm(Ac, Bc), ref)
