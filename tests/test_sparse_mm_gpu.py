@@ -728,6 +728,36 @@ def test_rewritten_index_memory_under_a_cached_pattern_is_detected(mode, monkeyp
     tsgu.clear_pattern_cache()
 
 
+def test_graph_capture_with_a_deferred_pattern_check_outstanding():
+    """The deferred checksum comparison must stay out of a CUDA graph capture: with a check in flight (launched by the
+    first reuse of the pattern, not yet collected) a capture of the next call has to succeed -- an event query inside
+    the capture would invalidate it, and bench.py would silently fall back to its eager region."""
+    import torchsparsegradutils_b200 as tsgu
+    from torchsparsegradutils_b200 import sparse_mm
+    from torchsparsegradutils_b200._pattern import csr_pattern
+
+    tsgu.clear_pattern_cache()
+    A = rand_csr(300, 200, 5, seed=3)
+    B = torch.randn(200, 16, device=DEV)
+    ref = sparse_mm(A, B)       # miss: pattern built
+    sparse_mm(A, B)             # hit 1: deferred check launched
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        sparse_mm(A, B)
+    torch.cuda.current_stream().wait_stream(side)
+    pat = csr_pattern(A)
+    pat.pending_check = (torch.cuda.Event(), torch.zeros(4, dtype=torch.int64))  # a check that has not landed yet
+    pat.pending_check[0].record()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = sparse_mm(A, B)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    tsgu.clear_pattern_cache()
+
+
 def test_unsupported_value_dtype_is_a_runtime_error():
     from torchsparsegradutils_b200 import sparse_mm
 

@@ -554,12 +554,16 @@ def _check_fingerprint(hit, index_tensors) -> None:
     prepares patterns ahead: bench.py's end-to-end leg, +1.5 ms per step); TSGU_B200_VERIFY_PATTERN=1 checks on the spot."""
     hits = hit.hits = getattr(hit, "hits", 0) + 1
     pending = getattr(hit, "pending_check", None)
+    if pending is None and not _verify_due(hits):
+        return
+    if index_tensors[0].is_cuda and torch.cuda.is_current_stream_capturing():
+        return  # nothing here may run during a graph capture (an event query alone invalidates it)
     if pending is not None and pending[0].query():
         hit.pending_check = None
         got = pending[1].tolist()
         if got[:len(got) // 2] != got[len(got) // 2:]:
             raise RuntimeError(_REWRITTEN + " (detected by a deferred check: results since the rewrite used the old pattern)")
-    if not _verify_due(hits) or (index_tensors[0].is_cuda and torch.cuda.is_current_stream_capturing()):
+    if not _verify_due(hits):
         return
     pair = torch.cat([hit.fingerprint, _fingerprint(*index_tensors)])
     if _VERIFY == "1" or not pair.is_cuda:
