@@ -78,9 +78,10 @@ TSGU_API int tsgu_set_sm_margin(int sms);
 /* Host mailbox: `bytes` of mapped pinned host memory (host_ptr for the host to read, dev_ptr for kernels to write) and
  * tsgu_publish(), a one-block kernel that stores `bytes` (multiple of 4) of device memory `src` into a mailbox on
  * `stream`.  Synchronise the stream, then read host_ptr.  This is how the host side learns the few scalars a new
- * sparsity pattern produces (longest row, window-plan verdict, padded size -- the reference gets the same facts from
- * `.item()`-style reads inside torch.sparse.mm's planning): unlike a cudaMemcpy the store does not queue behind bulk
- * D2H transfers on the copy engines. */
+ * sparsity pattern produces (longest row, window-plan verdict, padded size).  Replaces the `.item()` / `int(tensor)`
+ * host reads of the reference's index plumbing (utils/utils.py:766-767 in sparse_block_diag_split, and the nnz / shape
+ * reads inside the torch.sparse.mm calls of sparse_matmul.py:155 and :229): unlike a cudaMemcpy the store does not queue
+ * behind bulk D2H transfers on the copy engines. */
 TSGU_API int tsgu_mailbox_create(size_t bytes, void** host_ptr, void** dev_ptr);
 TSGU_API int tsgu_mailbox_destroy(void* host_ptr);
 TSGU_API int tsgu_publish(const void* src, void* mailbox_dev, size_t bytes, void* stream);
@@ -220,7 +221,10 @@ TSGU_API int tsgu_scatter_values(const void* in, const void* perm, void* out, in
 
 /* *out (uint64, zeroed by the caller) += position-weighted checksum of an index array of `count` elements.  The host
  * side keeps one per cached sparsity pattern and re-checks it on a thinning schedule of cache hits, so index buffers that
- * were rewritten in place under a cached pattern raise instead of silently reusing the old structure. */
+ * were rewritten in place under a cached pattern raise instead of silently reusing the old structure.  No reference
+ * counterpart: the reference re-derives all index structure on every call (sparse_matmul.py:190-192 row expansion,
+ * :229 re-sort inside torch.sparse.mm(A.t(), .)), so it has nothing to invalidate; this is the guard that makes caching
+ * those structures safe. */
 TSGU_API int tsgu_fingerprint(const void* data, int64_t count, int idx_dtype, void* out, void* stream);
 
 /* Batched CSR (crow (b, n+1), col (b, nnz)) -> block-diagonal CSR over b*n rows / b*m columns in one pass: the index
